@@ -1,0 +1,146 @@
+/*
+ * w2l.h — C-ABI of the B200-native Wav2Lip compute core (libw2l.so).
+ *
+ * The reference (Rudrabha/Wav2Lip) has no FFI: its boundary is the Python module surface
+ * `models` / `audio` that the scripts import by bare name.  Each entry point below replaces
+ * one of those Python call targets; the reference-side binding (a ctypes-backed `models`
+ * package with the same class names, ctor/forward signatures and state_dict keys) lives in
+ * wav2lip_b200/models/ and is described in INTEGRATION.md.
+ *
+ * Conventions
+ *  - plain C types only: pointers, sizes, ints.  No torch / C++ types cross this boundary.
+ *  - every function returns 0 on success, a negative W2L_E* code on failure; the message is
+ *    available through w2l_last_error() (thread local).  Nothing throws across the ABI.
+ *  - "dev" pointers are CUDA device pointers on the context's device; tensors are fp32,
+ *    contiguous, in the layout the reference's callers build (NCHW / 5-D B,C,T,H,W).
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); calls are
+ *    asynchronous on that stream unless stated otherwise.
+ *  - a context is bound to one device and is not thread safe (one context per GPU / stream).
+ *  - there is NO CPU fallback: every compute entry point fails with W2L_ENODEV when no
+ *    sm_100 device is usable.
+ */
+#ifndef W2L_H_
+#define W2L_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define W2L_ABI_VERSION 1
+
+/* error codes */
+#define W2L_OK        0
+#define W2L_EINVAL   -1   /* bad argument / shape */
+#define W2L_ENODEV   -2   /* no usable sm_100 CUDA device */
+#define W2L_ECUDA    -3   /* CUDA runtime / driver error (see w2l_last_error) */
+#define W2L_ENOMEM   -4
+#define W2L_ESTATE   -5   /* e.g. forward before weights were loaded */
+
+/* networks */
+#define W2L_NET_GENERATOR 0   /* models.Wav2Lip            /root/reference/models/wav2lip.py:8-125   */
+#define W2L_NET_SYNCNET   1   /* models.SyncNet_color      /root/reference/models/syncnet.py:7-66    */
+#define W2L_NET_DISC      2   /* models.Wav2Lip_disc_qual  /root/reference/models/wav2lip.py:127-184 */
+
+/* block kinds — /root/reference/models/conv.py */
+#define W2L_BLOCK_CONV_BN_RELU   0   /* Conv2d           conv.py:5-19  */
+#define W2L_BLOCK_CONVT_BN_RELU  1   /* Conv2dTranspose  conv.py:33-44 */
+#define W2L_BLOCK_CONV_LRELU     2   /* nonorm_Conv2d    conv.py:21-31 */
+#define W2L_BLOCK_CONV_PLAIN     3   /* bare nn.Conv2d heads: wav2lip.py:84, :152 (followed by Sigmoid) */
+
+/* operand precision of the tensor-core path (accumulation is always fp32) */
+#define W2L_PREC_F16  0   /* fp16 operands: 10-bit mantissa, same as TF32 (default) */
+#define W2L_PREC_BF16 1   /* bf16 operands: for checkpoints whose activations exceed the fp16 range */
+
+typedef struct w2l_ctx w2l_ctx;
+
+/* One row of an architecture table: a conv block with the reference's own module path. */
+typedef struct w2l_layer_info {
+    char name[64];      /* e.g. "face_decoder_blocks.3.1" — state_dict prefix of the block */
+    int32_t kind;       /* W2L_BLOCK_* */
+    int32_t cin, cout;
+    int32_t kh, kw, sh, sw, ph, pw;
+    int32_t out_pad;    /* ConvTranspose2d output_padding */
+    int32_t residual;   /* conv.py:16-18 */
+} w2l_layer_info;
+
+/* ---- introspection (host only; usable without a GPU) ---- */
+int         w2l_abi_version(void);
+const char* w2l_last_error(void);
+int         w2l_net_num_layers(int net);
+int         w2l_net_layer_info(int net, int index, w2l_layer_info* out);
+
+/* ---- context ---- */
+/* Replaces `Model().to(device)` (inference.py:169,178; wav2lip_train.py:356). */
+int w2l_create(int device, int precision, w2l_ctx** out);
+int w2l_destroy(w2l_ctx* ctx);
+
+/* Replaces `model.load_state_dict(sd)` (inference.py:176): hands the context the fp32 device
+ * tensors of one network by their reference state_dict names ("<block>.conv_block.0.weight",
+ * "<block>.conv_block.1.running_var", "output_block.1.weight", ...).  Weights are re-packed
+ * (fp16/bf16, tap-major K-major tiles; BatchNorm running stats folded into per-channel
+ * scale/shift) on `stream`; the source tensors may be freed afterwards.  Re-callable.
+ * Unknown names are ignored ("...num_batches_tracked"); a missing tensor is W2L_EINVAL. */
+int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* names,
+                     const void* const* dev_ptrs, const int64_t* numels, void* stream);
+
+/* Replaces `Wav2Lip.forward(audio_sequences, face_sequences)` (wav2lip.py:87-125), eval mode.
+ *   T == 0 : mel (B,1,80,16), face (B,6,96,96)      -> out (B,3,96,96)
+ *   T  > 0 : mel (B,T,1,80,16), face (B,6,T,96,96)  -> out (B,3,T,96,96)   (t-major flatten inside) */
+int w2l_generator_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_dev, float* out_dev,
+                          int B, int T, void* stream);
+
+/* Same, with HOST buffers: H2D of the inputs, forward, D2H of the result, then a stream sync.
+ * Buffers should be pinned for full PCIe bandwidth (pageable memory works, slower). */
+int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_host, const float* face_host,
+                               float* out_host, int B, int T);
+
+/* Replaces `SyncNet_color.forward(audio, face)` (syncnet.py:55-66):
+ *   mel (B,1,80,16), face (B,15,48,96) -> audio_emb (B,512), face_emb (B,512), both L2-normalised. */
+int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_dev,
+                        float* audio_emb_dev, float* face_emb_dev, int B, void* stream);
+
+/* Replaces `Wav2Lip_disc_qual.forward(face_sequences)` (wav2lip.py:176-184):
+ *   frames (B,3,T,96,96) -> prob (B*T,1), rows t-major (row = t*B + b). */
+int w2l_disc_forward(w2l_ctx* ctx, const float* frames_dev, float* prob_dev, int B, int T, void* stream);
+
+/* Replaces one `models.conv.{Conv2d,Conv2dTranspose,nonorm_Conv2d}.forward` (conv.py:15-19,29-31,
+ * 42-44), eval mode — the operator-level entry used by the per-geometry parity tests.
+ *   x (N,cin,H,W) fp32 -> y (N,cout,Hout,Wout) fp32.  weight is (cout,cin,kh,kw), or
+ *   (cin,cout,kh,kw) for the transposed block; bn_* are NULL for nonorm/plain blocks. */
+int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec,
+                           const float* x_dev, int N, int H, int W,
+                           const float* weight_dev, const float* bias_dev,
+                           const float* bn_weight_dev, const float* bn_bias_dev,
+                           const float* bn_mean_dev, const float* bn_var_dev,
+                           float* y_dev, void* stream);
+
+/* Debug/test aid: copy the output of block `layer` (index into the net's table) of the LAST
+ * forward of `net` to y (N,cout,H,W) fp32.  *h,*w,*c receive the dims (any may be NULL). */
+int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y_dev, int* n, int* c, int* h, int* w,
+                           void* stream);
+
+/* Replaces `audio.melspectrogram(wav)` (audio.py:45-51 with hparams.py:33-73):
+ *   wav (L) fp32 -> mel (80, 1 + L/200) fp32 in [-4,4], row-major as numpy returns it.
+ *   L must be > 400 (reflect padding), as librosa requires. */
+int w2l_melspectrogram(w2l_ctx* ctx, const float* wav_dev, int64_t n_samples, float* mel_dev, void* stream);
+int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_host, int64_t n_samples, float* mel_host);
+/* number of frames for n_samples: 1 + n_samples/200 (librosa center=True) */
+int64_t w2l_mel_num_frames(int64_t n_samples);
+
+/* ---- instrumentation ---- */
+/* kernels launched by this library since the context was created (all streams) */
+int64_t w2l_launch_count(const w2l_ctx* ctx);
+/* bytes of device memory currently held by the context (weights + activation arenas) */
+int64_t w2l_device_bytes(const w2l_ctx* ctx);
+/* Time the conv kernels of the last-built plan of `net` individually: runs every launch `iters`
+ * times with CUDA events on `stream` and writes per-launch mean milliseconds and flop counts.
+ * Returns the number of launches written (<= cap). */
+int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out,
+                     char (*names_out)[64], void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* W2L_H_ */

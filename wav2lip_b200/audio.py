@@ -1,0 +1,74 @@
+"""Mirror of the reference's `audio.melspectrogram` (/root/reference/audio.py:45-51) on the GPU.
+
+`melspectrogram(wav)` keeps the reference's contract — a 1-D float array of 16 kHz samples in,
+a float32 (80, 1 + len(wav)//200) array in [-4, 4] out — and additionally accepts a CUDA tensor
+(then returns a CUDA tensor and never touches the host).  Constants are hparams.py:33-73; they are
+baked into the kernel, there is no `hparams` object to mutate.
+
+The rest of audio.py (load_wav resampling, save_wav, the inverse transforms) is outside the hot
+path and not provided.  As in the reference (wav2lip_train.py:139-141 runs it inside DataLoader
+workers), note that a CUDA-backed function must not be called from forked worker processes.
+"""
+import ctypes as C
+import importlib
+import os
+import sys
+
+import numpy as np
+
+
+def _lib():
+    try:
+        return importlib.import_module("wav2lip_b200._lib")
+    except ModuleNotFoundError:
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        if root not in sys.path:
+            sys.path.append(root)
+        return importlib.import_module("wav2lip_b200._lib")
+
+
+_ctx = {}
+
+
+def _context(device: int):
+    L = _lib()
+    if device not in _ctx:
+        _ctx[device] = L.Context(device)
+    return _ctx[device]
+
+
+def num_frames(n_samples: int) -> int:
+    return 1 + int(n_samples) // 200
+
+
+def melspectrogram(wav, device: int = 0):
+    L = _lib()
+    try:
+        import torch
+        is_tensor = isinstance(wav, torch.Tensor)
+    except ImportError:  # pragma: no cover
+        is_tensor = False
+    if is_tensor:
+        if not wav.is_cuda:
+            wav = wav.detach().cpu().numpy()
+        else:
+            x = wav.detach().contiguous().float().reshape(-1)
+            ctx = _context(x.device.index or 0)
+            out = torch.empty((80, num_frames(x.numel())), device=x.device, dtype=torch.float32)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
+            L.check(ctx.lib.w2l_melspectrogram(ctx.h, C.c_void_p(x.data_ptr()), x.numel(), C.c_void_p(out.data_ptr()),
+                                               C.c_void_p(stream)))
+            return out
+    x = np.ascontiguousarray(np.asarray(wav, dtype=np.float32).reshape(-1))
+    ctx = _context(device)
+    out = np.empty((80, num_frames(x.shape[0])), dtype=np.float32)
+    L.check(ctx.lib.w2l_melspectrogram_host(ctx.h, x.ctypes.data_as(C.c_void_p), x.shape[0], out.ctypes.data_as(C.c_void_p)))
+    return out
+
+
+def mel_basis() -> np.ndarray:
+    """The kernel's own (80, 401) Slaney filterbank (host computation in libw2l), for inspection."""
+    L = _lib()
+    out = np.empty((80, 401), dtype=np.float32)
+    L.check(L.get_lib().w2l_mel_basis_host(out.ctypes.data_as(C.c_void_p)))
+    return out

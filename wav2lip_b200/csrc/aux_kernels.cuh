@@ -1,0 +1,160 @@
+// aux_kernels.cuh — the small data-movement / packing kernels around the conv kernel.
+//   ingest:   fp32 NCHW / 5-D caller tensors -> NHWC 16-bit with channel padding, t-major flatten
+//             (wav2lip.py:93-94, :158-161) and the lower-half crop (wav2lip.py:155-156) as index math.
+//   pack_w:   fp32 conv / convT weights -> [tap][Cout_pad][Cin_pad] 16-bit K-major slabs.
+//   fold_bn:  conv bias + BatchNorm running stats (conv.py:8-11, eps 1e-5) -> per-channel scale/shift.
+//   l2norm:   F.normalize(p=2, dim=1) of syncnet.py:62-63.
+//   disc_head: Conv2d(512,1,1) + Sigmoid of wav2lip.py:152.
+//   export:   NHWC 16-bit slice -> NCHW fp32 (tests / debug only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace w2l {
+
+template <bool kBF16>
+__device__ __forceinline__ uint16_t to16(float f) {
+    if constexpr (kBF16) {
+        __nv_bfloat16 h = __float2bfloat16_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+    } else {
+        __half h = __float2half_rn(f);
+        return *reinterpret_cast<uint16_t*>(&h);
+    }
+}
+template <bool kBF16>
+__device__ __forceinline__ float from16(uint16_t u) {
+    if constexpr (kBF16) {
+        return __bfloat162float(*reinterpret_cast<__nv_bfloat16*>(&u));
+    } else {
+        return __half2float(*reinterpret_cast<__half*>(&u));
+    }
+}
+
+struct IngestParams {
+    const float* src;
+    uint16_t* dst;      // [N][H][W][Cpad]
+    int N, B;           // n = t*B + b
+    int C, H, W, Cpad;
+    long long sB, sC, sT;  // source strides in elements for b, c, t
+    int y_off, Wsrc;       // source row offset / row pitch
+};
+
+template <bool kBF16>
+__global__ void ingest_kernel(const IngestParams p) {
+    const long long total = (long long)p.N * p.H * p.W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % p.W);
+        const int y = (int)((i / p.W) % p.H);
+        const int n = (int)(i / ((long long)p.W * p.H));
+        const int b = n % p.B, t = n / p.B;
+        const float* s = p.src + b * p.sB + t * p.sT + (long long)(y + p.y_off) * p.Wsrc + x;
+        uint16_t* d = p.dst + i * p.Cpad;
+        for (int c0 = 0; c0 < p.Cpad; c0 += 8) {
+            uint16_t h[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                h[j] = (c < p.C) ? to16<kBF16>(__ldg(s + c * p.sC)) : (uint16_t)0;
+            }
+            uint4 o;
+            o.x = h[0] | ((uint32_t)h[1] << 16);
+            o.y = h[2] | ((uint32_t)h[3] << 16);
+            o.z = h[4] | ((uint32_t)h[5] << 16);
+            o.w = h[6] | ((uint32_t)h[7] << 16);
+            *reinterpret_cast<uint4*>(d + c0) = o;
+        }
+    }
+}
+
+// NHWC 16-bit (channel slice of a buffer with channel pitch Cs) -> NCHW fp32
+template <bool kBF16>
+__global__ void export_kernel(const uint16_t* src, float* dst, int N, int H, int W, int C, int Cs, int f32src) {
+    const long long total = (long long)N * C * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const int y = (int)((i / W) % H);
+        const int c = (int)((i / ((long long)W * H)) % C);
+        const int n = (int)(i / ((long long)W * H * C));
+        const long long so = (((long long)n * H + y) * W + x) * Cs + c;
+        dst[i] = f32src ? reinterpret_cast<const float*>(src)[so] : from16<kBF16>(src[so]);
+    }
+}
+
+struct PackParams {
+    const float* src;
+    uint16_t* dst;  // [ntaps][cout_pad][cin_pad]
+    int ntaps, cout, cin, cout_pad, cin_pad;
+    long long s_co, s_ci, s_r, s_s;  // source strides (elements)
+    signed char r[49], s[49];        // filter coordinates of each packed tap
+};
+
+template <bool kBF16>
+__global__ void pack_w_kernel(const PackParams p) {
+    const long long total = (long long)p.ntaps * p.cout_pad * p.cin_pad;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(i % p.cin_pad);
+        const int co = (int)((i / p.cin_pad) % p.cout_pad);
+        const int t = (int)(i / ((long long)p.cin_pad * p.cout_pad));
+        float v = 0.0f;
+        if (ci < p.cin && co < p.cout) v = p.src[co * p.s_co + ci * p.s_ci + p.r[t] * p.s_r + p.s[t] * p.s_s];
+        p.dst[i] = to16<kBF16>(v);
+    }
+}
+
+// scale/shift of length reps*cout (replicated), padded with (0,0) up to n_pad
+__global__ void fold_bn_kernel(const float* bias, const float* gamma, const float* beta, const float* mean,
+                               const float* var, float eps, int cout, int reps, int n_pad, float* scale,
+                               float* shift) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad) return;
+    if (i >= cout * reps) {
+        scale[i] = 0.0f;
+        shift[i] = 0.0f;
+        return;
+    }
+    const int c = i % cout;
+    const float b = bias ? bias[c] : 0.0f;
+    if (gamma) {
+        const float s = gamma[c] / sqrtf(var[c] + eps);
+        scale[i] = s;
+        shift[i] = (b - mean[c]) * s + beta[c];
+    } else {
+        scale[i] = 1.0f;
+        shift[i] = b;
+    }
+}
+
+// one warp per row of a (B, D) fp32 matrix: y = x / max(||x||_2, 1e-12)
+__global__ void l2norm_kernel(const float* x, float* y, int B, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float* xr = x + (long long)row * D;
+    float s = 0.0f;
+    for (int i = lane; i < D; i += 32) s = fmaf(xr[i], xr[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / fmaxf(sqrtf(s), 1e-12f);
+    for (int i = lane; i < D; i += 32) y[(long long)row * D + i] = xr[i] * inv;
+}
+
+// one warp per row: prob = sigmoid(dot(x[row,:D], w) + b), x is 16-bit
+template <bool kBF16>
+__global__ void disc_head_kernel(const uint16_t* x, const float* w, const float* b, float* prob, int rows, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float s = 0.0f;
+    for (int i = lane; i < D; i += 32) s = fmaf(from16<kBF16>(x[(long long)row * D + i]), w[i], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) prob[row] = 1.0f / (1.0f + __expf(-(s + b[0])));
+}
+
+}  // namespace w2l

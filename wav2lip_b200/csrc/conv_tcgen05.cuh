@@ -1,0 +1,424 @@
+// conv_tcgen05.cuh — the fused conv-block kernel of the Wav2Lip hot path for sm_100a.
+//
+// One persistent, warp-specialised kernel computes, for every block kind of
+// /root/reference/models/conv.py (Conv2d :5-19, nonorm_Conv2d :21-31 and, phase by phase,
+// Conv2dTranspose :33-44):
+//
+//     y = act( scale[c] * conv(x, w)[., c] + shift[c]  (+ residual) )
+//
+// as an implicit GEMM on the 5th-generation tensor cores:
+//     M = output pixels (a 128-row tile = a bw x bh x bn box of the NHWC output grid),
+//     N = output channels (BN per tile), K = filter taps x input channels (BK per step).
+//
+//   warp 0  : TMA producer. For each K step one 4-D tiled TMA load brings the input box of the
+//             current filter tap (start coordinate = tile origin * stride + tap offset; out-of-bounds
+//             coordinates are zero-filled by the TMA unit, which IS the conv zero padding) and one
+//             3-D TMA load brings the [BN x BK] weight slice of that tap. Both land K-major with the
+//             hardware 128/64/32-byte swizzle that the UMMA shared-memory descriptors expect.
+//   warp 1  : MMA issuer. One lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//             accumulating in TMEM (fp32); tcgen05.commit releases smem stages / publishes the tile.
+//   warp 2  : TMEM allocator (2 accumulator stages x BN columns, so the epilogue of tile i overlaps
+//             the main loop of tile i+1).
+//   warps 4-7: epilogue. tcgen05.ld the accumulator (lane = GEMM row = output pixel), apply the folded
+//             BatchNorm scale/shift (conv bias folded in), the residual add (conv.py:16-18: after BN,
+//             before ReLU), ReLU / LeakyReLU(0.01), convert and store NHWC straight into the channel
+//             slice of the consumer's buffer (so torch.cat of wav2lip.py:108 never exists). The
+//             generator head (1x1 conv 32->3 + sigmoid, wav2lip.py:84-85) is fused for the last block.
+//
+// Everything a launch needs is in ConvParams (a __grid_constant__), built once per plan on the host.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+
+namespace w2l {
+
+constexpr int kTileM = 128;
+constexpr int kMaxTaps = 49;
+constexpr int kConvThreads = 256;
+constexpr int kSmemBudget = 200 * 1024;  // pipeline stages; barriers etc. live in the extra KB below
+constexpr int kSmemExtra = 2048;         // 1024 alignment slack + barriers
+
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA;  // activations, dims (C, W, H, N), box (BK, bw*sx, bh*sy, bn), elem strides (1,sx,sy,1)
+    CUtensorMap tmB;  // weights, dims (Cin_pad, Cout_pad, taps), box (BK, BN, 1)
+    // M tiling of the logical output grid
+    int tiles_x, tiles_y, tiles_n, n_tiles;
+    int bw, bh, bn;
+    int sx, sy;
+    int Wout, Hout, N;
+    // K loop
+    int ntaps, kc_per_tap;
+    unsigned stage_tx_bytes;  // bytes both TMA loads of one stage deliver
+    // epilogue
+    int act;
+    int out_f32;
+    void* out;              // element (n,y,x,c) at out + n*out_sn + y*out_sy + x*out_sx + c  (elements)
+    long long out_sn, out_sy, out_sx;
+    const void* res;        // nullptr = no residual; same addressing
+    long long res_sn, res_sy, res_sx;
+    const float* scale;     // [n_tiles*BN]
+    const float* shift;
+    // fused generator head (kHead kernels only): out = sigmoid(W[3x32] relu(y) + b), fp32 NCHW/5-D
+    const float* head_w;
+    const float* head_b;
+    float* head_out;
+    int head_B, head_T;     // n = t*head_B + b ; T=1,B=N for the 4-D call
+    signed char dx[kMaxTaps];
+    signed char dy[kMaxTaps];
+};
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "W2L_WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra W2L_DONE_%=;\n\t"
+        "bra W2L_WAIT_%=;\n\t"
+        "W2L_DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* desc) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(desc)) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2,
+                                            int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major operand tile in shared memory: rows of BK*2 bytes, 8-row groups, hardware swizzle = row bytes.
+template <int BK>
+__device__ __forceinline__ uint64_t make_kmajor_desc(uint32_t saddr) {
+    constexpr uint64_t kLayout = (BK == 64) ? 2 : (BK == 32) ? 4 : 6;  // SWIZZLE_128B / 64B / 32B
+    constexpr uint64_t kSBO = (8 * BK * 2) >> 4;                       // bytes between 8-row groups >> 4
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4);  // start address      [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                  // leading byte offset [16,30) (unused, K-major swizzled)
+    d |= kSBO << 32;                                      // stride byte offset  [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                  // descriptor version  [46,48) = 1 on sm_100
+    d |= kLayout << 61;                                   // layout type         [61,64)
+    return d;
+}
+
+template <int BN, bool kBF16>
+__device__ __forceinline__ constexpr uint32_t make_idesc() {
+    // cute::UMMA::InstrDescriptor: c_format [4,6)=1 (F32); a_format [7,10), b_format [10,13): 0=F16 1=BF16;
+    // a_major [15], b_major [16] = 0 (K-major); n_dim [17,23) = N>>3; m_dim [24,29) = M>>4.
+    return (1u << 4) | ((kBF16 ? 1u : 0u) << 7) | ((kBF16 ? 1u : 0u) << 10) | (static_cast<uint32_t>(BN >> 3) << 17) |
+           (static_cast<uint32_t>(kTileM >> 4) << 24);
+}
+
+template <int BN, int BK>
+struct ConvCfg {
+    static constexpr int kABytes = kTileM * BK * 2;
+    static constexpr int kBBytes = BN * BK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemExtra;
+    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+    static_assert(kStages >= 2, "need a pipeline");
+};
+
+template <bool kBF16>
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if constexpr (kBF16) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    } else {
+        __half2 h = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&h);
+    }
+}
+template <bool kBF16>
+__device__ __forceinline__ float2 unpack2(uint32_t u) {
+    if constexpr (kBF16) {
+        return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    } else {
+        return __half22float2(*reinterpret_cast<__half2*>(&u));
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------------
+template <int BN, int BK, bool kBF16, bool kHead>
+__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BN, BK>;
+    constexpr int kStages = Cfg::kStages;
+    static_assert(!kHead || BN == 32, "fused head expects the 32-channel output block");
+
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-B alignment
+    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&p.tmA);
+        tma_prefetch_desc(&p.tmB);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull_bar(a), 1);
+            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+        }
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+    const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int total_tiles = m_tiles * p.n_tiles;
+    const int k_steps = p.ntaps * p.kc_per_tap;
+
+    if (warp == 0) {
+        // =============================== TMA producer ===============================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                const int m = tile / p.n_tiles;
+                const int tx = m % p.tiles_x;
+                const int ty = (m / p.tiles_x) % p.tiles_y;
+                const int tn = m / (p.tiles_x * p.tiles_y);
+                const int x_in0 = tx * p.bw * p.sx;
+                const int y_in0 = ty * p.bh * p.sy;
+                const int n0 = tn * p.bn;
+                for (int t = 0; t < p.ntaps; ++t) {
+                    const int cx = x_in0 + p.dx[t];
+                    const int cy = y_in0 + p.dy[t];
+                    for (int kc = 0; kc < p.kc_per_tap; ++kc) {
+                        mbar_wait(empty_bar(stage), phase ^ 1u);
+                        const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
+                        const uint32_t b_dst = a_dst + Cfg::kABytes;
+                        mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
+                        tma_load_4d(a_dst, &p.tmA, full_bar(stage), kc * BK, cx, cy, n0);
+                        tma_load_3d(b_dst, &p.tmB, full_bar(stage), kc * BK, nt * BN, t);
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // =============================== MMA issuer ===============================
+        constexpr uint32_t idesc = make_idesc<BN, kBF16>();
+        int stage = 0;
+        uint32_t phase = 0;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int ks = 0; ks < k_steps; ++ks) {
+                mbar_wait(full_bar(stage), phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
+                    const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
+                    const uint64_t bdesc = make_kmajor_desc<BK>(a_addr + Cfg::kABytes);
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // advance 32 B (16 elements) along K inside the swizzle atom: +2 in the >>4 address field
+                        tc_mma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0 ? 1u : 0u);
+                    }
+                    tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
+                    if (ks == k_steps - 1) tc_commit(tfull_bar(acc));
+                }
+                __syncwarp();
+                if (++stage == kStages) { stage = 0; phase ^= 1u; }
+            }
+        }
+    } else if (warp >= 4) {
+        // =============================== epilogue ===============================
+        const int q = warp - 4;            // TMEM lane quarter this warp may access (warp id % 4)
+        const int row = q * 32 + lane;     // GEMM row == pixel index inside the tile box
+        const int rows_valid = p.bw * p.bh * p.bn;
+        const int px = row % p.bw;
+        const int py = (row / p.bw) % p.bh;
+        const int pn = row / (p.bw * p.bh);
+        constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld batch
+        int it = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            const int nt = tile % p.n_tiles;
+            const int m = tile / p.n_tiles;
+            const int tx = m % p.tiles_x;
+            const int ty = (m / p.tiles_x) % p.tiles_y;
+            const int tn = m / (p.tiles_x * p.tiles_y);
+            const int x = tx * p.bw + px;
+            const int y = ty * p.bh + py;
+            const int n = tn * p.bn + pn;
+            const bool valid = (row < rows_valid) && (x < p.Wout) && (y < p.Hout) && (n < p.N);
+
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const long long o_off = (long long)n * p.out_sn + (long long)y * p.out_sy + (long long)x * p.out_sx;
+            const long long r_off = (long long)n * p.res_sn + (long long)y * p.res_sy + (long long)x * p.res_sx;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += CH) {
+                uint32_t v[CH];
+                tmem_ld16(taddr + c0, v);
+                if constexpr (CH == 32) tmem_ld16(taddr + c0 + 16, v + 16);
+                tmem_ld_wait();
+                if (valid) {
+                    const int cg = nt * BN + c0;  // first output channel of this batch
+                    float f[CH];
+#pragma unroll
+                    for (int j = 0; j < CH; j += 4) {
+                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cg + j));
+                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cg + j));
+                        f[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x);
+                        f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+                        f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+                        f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+                    }
+                    if (p.res != nullptr) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(
+                            reinterpret_cast<const uint16_t*>(p.res) + r_off + cg);
+#pragma unroll
+                        for (int j = 0; j < CH / 8; ++j) {
+                            const uint4 r = __ldg(rp + j);
+                            const float2 a = unpack2<kBF16>(r.x), b = unpack2<kBF16>(r.y);
+                            const float2 c = unpack2<kBF16>(r.z), d = unpack2<kBF16>(r.w);
+                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                        }
+                    }
+                    if (p.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.0f);
+                    } else if (p.act == ACT_LRELU) {
+#pragma unroll
+                        for (int j = 0; j < CH; ++j) f[j] = f[j] > 0.0f ? f[j] : 0.01f * f[j];
+                    }
+                    if constexpr (kHead) {
+                        // wav2lip.py:84-85: Conv2d(32,3,1) + Sigmoid on the fp32 block output still in registers
+                        const int hb = n % p.head_B, ht = n / p.head_B;
+                        const long long plane = (long long)p.Hout * p.Wout;
+#pragma unroll
+                        for (int oc = 0; oc < 3; ++oc) {
+                            float s = __ldg(p.head_b + oc);
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) s = fmaf(f[j], __ldg(p.head_w + oc * 32 + j), s);
+                            s = 1.0f / (1.0f + __expf(-s));
+                            p.head_out[(((long long)hb * 3 + oc) * p.head_T + ht) * plane + (long long)y * p.Wout + x] = s;
+                        }
+                    } else if (p.out_f32) {
+                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_off + cg);
+#pragma unroll
+                        for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                    } else {
+                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o_off + cg);
+#pragma unroll
+                        for (int j = 0; j < CH / 8; ++j) {
+                            uint4 o;
+                            o.x = pack2<kBF16>(f[8 * j + 0], f[8 * j + 1]);
+                            o.y = pack2<kBF16>(f[8 * j + 2], f[8 * j + 3]);
+                            o.z = pack2<kBF16>(f[8 * j + 4], f[8 * j + 5]);
+                            o.w = pack2<kBF16>(f[8 * j + 6], f[8 * j + 7]);
+                            op[j] = o;
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+}
+
+}  // namespace w2l

@@ -1,0 +1,1181 @@
+// w2l_api.cu — host side of libw2l.so: the C-ABI of include/w2l.h, the per-batch-size execution plans
+// (buffers, TMA tensor maps, kernel parameters) and the launch loops.  No torch, no CPU compute path.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/w2l.h"
+#include "aux_kernels.cuh"
+#include "conv_tcgen05.cuh"
+#include "mel.cuh"
+#include "netspec.h"
+
+using namespace w2l;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(W2L_ECUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+#define CKR(expr)               \
+    do {                        \
+        int r_ = (expr);        \
+        if (r_ != W2L_OK) return r_; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// specs (built once, host only)
+// ------------------------------------------------------------------------------------------------
+static const GeneratorSpec& gen_spec() { static GeneratorSpec s = build_generator_spec(); return s; }
+static const SyncnetSpec& sync_spec() { static SyncnetSpec s = build_syncnet_spec(); return s; }
+static const DiscSpec& disc_spec() { static DiscSpec s = build_disc_spec(); return s; }
+static const std::vector<Layer>* net_layers(int net) {
+    switch (net) {
+        case W2L_NET_GENERATOR: return &gen_spec().layers;
+        case W2L_NET_SYNCNET: return &sync_spec().layers;
+        case W2L_NET_DISC: return &disc_spec().layers;
+    }
+    return nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// driver entry point for tensor-map encoding (no link-time dependency on libcuda)
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// ------------------------------------------------------------------------------------------------
+// tensors in HBM
+// ------------------------------------------------------------------------------------------------
+// Activations are NHWC, 16-bit (fp16 or bf16), channel pitch Cs; a view may select a channel slice
+// [c_off, c_off + C) of a wider buffer (the skip-concat buffers of the decoder).
+struct Act {
+    uint16_t* base = nullptr;  // start of the buffer (not of the slice)
+    int N = 0, H = 0, W = 0;
+    int Cs = 0;     // channel pitch of the buffer
+    int c_off = 0;  // first channel of this view
+    int C = 0;      // channels of this view
+    bool f32 = false;
+    uint16_t* ptr() const { return base + c_off; }
+    Act slice(int off, int c) const { Act a = *this; a.c_off = c_off + off; a.C = c; return a; }
+};
+
+struct PackedW {
+    uint16_t* w = nullptr;  // [ntaps][cout_pad][cin_pad]
+    int ntaps = 0, cout_pad = 0, cin_pad = 0;
+    std::vector<signed char> dx, dy;  // input offset of each tap relative to (out * stride)
+    int py = 0, px = 0;               // output phase (transposed conv)
+};
+
+struct LayerW {
+    std::vector<PackedW> ph;  // 1 for conv, 4 for stride-2 convT, 1 (as GEMM) for the 1x1->3x3 convT
+    float* scale = nullptr;
+    float* shift = nullptr;
+    int n_scale = 0;
+    bool gemm_convT = false;
+    bool loaded = false;
+};
+
+struct NetW {
+    std::vector<LayerW> layers;
+    float* head_w = nullptr;  // generator output_block.1 (3x32) / disc binary_pred (512)
+    float* head_b = nullptr;
+    bool loaded = false;
+};
+
+enum OpType { OP_CONV = 0, OP_INGEST = 1, OP_L2NORM = 2, OP_DISC_HEAD = 3 };
+
+struct Op {
+    int type = OP_CONV;
+    std::string name;
+    // conv
+    ConvParams cp;
+    int BN = 0, BK = 0;
+    bool head = false;
+    int grid = 0;
+    double flops = 0;  // algorithmic (true MACs*2), not padded
+    // ingest
+    IngestParams ip;
+    int ingest_src = 0;  // which caller tensor: 0 = mel / frames, 1 = face
+    // l2norm / disc head
+    const void* aux_in = nullptr;
+    int aux_rows = 0, aux_dim = 0;
+    int aux_out = 0;  // which caller output
+};
+
+struct Plan {
+    int net = 0, B = 0, T = 0, N = 0;
+    std::vector<Op> ops;
+    std::vector<void*> allocs;
+    size_t bytes = 0;
+    std::map<int, Act> layer_out;  // layer index -> activation view (debug export)
+};
+
+struct w2l_ctx {
+    int device = 0;
+    bool bf16 = false;
+    int num_sms = 148;
+    bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
+    NetW nets[3];
+    std::map<std::string, std::unique_ptr<Plan>> plans;
+    Plan* last_plan[3] = {nullptr, nullptr, nullptr};
+    int64_t launches = 0;
+    size_t weight_bytes = 0;
+    // host-buffer entry points
+    cudaStream_t stream = nullptr;
+    void* stage[3] = {nullptr, nullptr, nullptr};
+    size_t stage_bytes[3] = {0, 0, 0};
+    // mel tables
+    double2* mel_tw = nullptr;
+    float* mel_bvals = nullptr;
+    int* mel_boff = nullptr;
+    int* mel_bstart = nullptr;
+    int* mel_blen = nullptr;
+};
+
+static int dev_alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 16);
+    if (e != cudaSuccess) return fail(W2L_ENOMEM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    return W2L_OK;
+}
+
+static int plan_alloc(Plan* pl, void** p, size_t bytes) {
+    CKR(dev_alloc(p, bytes));
+    pl->allocs.push_back(*p);
+    pl->bytes += bytes;
+    return W2L_OK;
+}
+
+static int plan_act(Plan* pl, Act* a, int N, int H, int W, int C, bool f32 = false) {
+    void* p = nullptr;
+    const size_t bytes = (size_t)N * H * W * C * (f32 ? 4 : 2);
+    CKR(plan_alloc(pl, &p, bytes));
+    a->base = (uint16_t*)p;
+    a->N = N; a->H = H; a->W = W; a->Cs = C; a->c_off = 0; a->C = C; a->f32 = f32;
+    return W2L_OK;
+}
+
+static void free_plan(Plan* pl) {
+    for (void* p : pl->allocs) cudaFree(p);
+    pl->allocs.clear();
+}
+
+// ------------------------------------------------------------------------------------------------
+// conv kernel dispatch
+// ------------------------------------------------------------------------------------------------
+typedef void (*ConvKernelFn)(const ConvParams);
+struct ConvKernelEntry { int BN, BK; bool bf16, head; ConvKernelFn fn; int smem; bool attr_set; };
+
+#define W2L_CONV_ENTRY(BN_, BK_)                                                                                      \
+    {BN_, BK_, false, false, conv_igemm_kernel<BN_, BK_, false, false>, ConvCfg<BN_, BK_>::kSmemBytes, false},        \
+    {BN_, BK_, true, false, conv_igemm_kernel<BN_, BK_, true, false>, ConvCfg<BN_, BK_>::kSmemBytes, false}
+
+static ConvKernelEntry g_conv_kernels[] = {
+    W2L_CONV_ENTRY(16, 16), W2L_CONV_ENTRY(16, 32), W2L_CONV_ENTRY(16, 64),
+    W2L_CONV_ENTRY(32, 16), W2L_CONV_ENTRY(32, 32), W2L_CONV_ENTRY(32, 64),
+    W2L_CONV_ENTRY(64, 16), W2L_CONV_ENTRY(64, 32), W2L_CONV_ENTRY(64, 64),
+    W2L_CONV_ENTRY(128, 16), W2L_CONV_ENTRY(128, 32), W2L_CONV_ENTRY(128, 64),
+    {32, 16, false, true, conv_igemm_kernel<32, 16, false, true>, ConvCfg<32, 16>::kSmemBytes, false},
+    {32, 16, true, true, conv_igemm_kernel<32, 16, true, true>, ConvCfg<32, 16>::kSmemBytes, false},
+};
+
+static ConvKernelEntry* find_conv_kernel(int BN, int BK, bool bf16, bool head) {
+    for (auto& e : g_conv_kernels)
+        if (e.BN == BN && e.BK == BK && e.bf16 == bf16 && e.head == head) return &e;
+    return nullptr;
+}
+
+static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
+    ConvKernelEntry* e = find_conv_kernel(op.BN, op.BK, ctx->bf16, op.head);
+    if (!e) return fail(W2L_EINVAL, "no conv kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
+    if (!e->attr_set) {
+        CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));
+        e->attr_set = true;
+    }
+    e->fn<<<op.grid, kConvThreads, e->smem, st>>>(op.cp);
+    ctx->launches++;
+    return W2L_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// building one conv launch
+// ------------------------------------------------------------------------------------------------
+static int pick_bk(int cin_pad) { return (cin_pad % 64 == 0) ? 64 : (cin_pad % 32 == 0) ? 32 : 16; }
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+// The 128-row tile is a (bw x bh x bn) box of output pixels; choose the box with the least padding waste.
+static void pick_box(int W, int H, int N, int sx, int sy, int* bw, int* bh, int* bn) {
+    double best = 1e30;
+    int b_w = 1, b_h = 1, b_n = 1;
+    for (int w = 1; w <= std::min(W, kTileM); ++w) {
+        if (w * sx > 256) break;
+        for (int h = 1; h <= std::min(H, kTileM / w); ++h) {
+            if (h * sy > 256) break;
+            int n = std::min(kTileM / (w * h), std::max(N, 1));
+            if (n < 1) continue;
+            if (n > 256) n = 256;
+            const double tiles = (double)((W + w - 1) / w) * ((H + h - 1) / h) * ((N + n - 1) / n);
+            // prefer wide boxes (longer contiguous runs) on ties
+            const double cost = tiles - 1e-6 * w - 1e-9 * h;
+            if (cost < best) { best = cost; b_w = w; b_h = h; b_n = n; }
+        }
+    }
+    *bw = b_w; *bh = b_h; *bn = b_n;
+}
+
+struct ConvArgs {
+    std::string name;
+    Act in, out;
+    const PackedW* w = nullptr;
+    int sx = 1, sy = 1;        // input stride per logical output pixel
+    int Hl = 0, Wl = 0;        // logical output grid handled by this launch
+    int osy = 1, osx = 1;      // output pixel = logical * os + phase
+    int phy = 0, phx = 0;
+    const Act* res = nullptr;
+    const float* scale = nullptr;
+    const float* shift = nullptr;
+    int ch_off = 0;            // offset into scale/shift
+    int act = ACT_RELU;
+    int cout = 0;              // channels produced
+    double macs_per_pixel = 0; // true MACs per logical output pixel (for flop accounting)
+    // fused head
+    bool head = false;
+    const float* head_w = nullptr;
+    const float* head_b = nullptr;
+    int head_B = 1, head_T = 1;
+};
+
+static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    Op op;
+    op.type = OP_CONV;
+    op.name = a.name;
+    const PackedW& w = *a.w;
+    const int BK = pick_bk(w.cin_pad);
+    if (a.in.C != w.cin_pad) return fail(W2L_EINVAL, "%s: input view has %d channels, weights packed for %d", a.name.c_str(), a.in.C, w.cin_pad);
+    if (a.cout % 16 != 0) return fail(W2L_EINVAL, "%s: cout %d not a multiple of 16", a.name.c_str(), a.cout);
+    int bw, bh, bn;
+    pick_box(a.Wl, a.Hl, a.in.N, a.sx, a.sy, &bw, &bh, &bn);
+    const int tiles_x = (a.Wl + bw - 1) / bw, tiles_y = (a.Hl + bh - 1) / bh, tiles_n = (a.in.N + bn - 1) / bn;
+    const int m_tiles = tiles_x * tiles_y * tiles_n;
+    int BN = 16;
+    for (int cand : {128, 64, 32, 16})
+        if (a.cout % cand == 0) { BN = cand; break; }
+    if (a.head) BN = 32;
+    else
+        while (BN > 32 && m_tiles * (a.cout / BN) < ctx->num_sms && a.cout % (BN / 2) == 0) BN /= 2;
+    if (w.cout_pad % BN != 0) return fail(W2L_EINVAL, "%s: cout_pad %d vs BN %d", a.name.c_str(), w.cout_pad, BN);
+    op.BN = BN; op.BK = BK; op.head = a.head;
+
+    ConvParams& p = op.cp;
+    memset(&p, 0, sizeof(p));
+    const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)a.in.C, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.in.N};
+        cuuint64_t strides[3] = {(cuuint64_t)a.in.Cs * 2, (cuuint64_t)a.in.W * a.in.Cs * 2, (cuuint64_t)a.in.H * a.in.W * a.in.Cs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * a.sx), (cuuint32_t)(bh * a.sy), (cuuint32_t)bn};
+        cuuint32_t es[4] = {1, (cuuint32_t)a.sx, (cuuint32_t)a.sy, 1};
+        CUresult r = enc(&p.tmA, dt, 4, a.in.ptr(), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS)
+            return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(A) failed with %d (dims %d,%d,%d,%d box %d,%d,%d,%d)", a.name.c_str(), (int)r,
+                        a.in.C, a.in.W, a.in.H, a.in.N, BK, bw * a.sx, bh * a.sy, bn);
+    }
+    {
+        cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)w.ntaps};
+        cuuint64_t strides[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout_pad * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&p.tmB, dt, 3, w.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(B) failed with %d", a.name.c_str(), (int)r);
+    }
+    p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_n = tiles_n; p.n_tiles = a.cout / BN;
+    p.bw = bw; p.bh = bh; p.bn = bn;
+    p.sx = a.sx; p.sy = a.sy;
+    p.Wout = a.Wl; p.Hout = a.Hl; p.N = a.in.N;
+    p.ntaps = w.ntaps; p.kc_per_tap = w.cin_pad / BK;
+    p.stage_tx_bytes = (unsigned)(bw * bh * bn * BK * 2 + BN * BK * 2);
+    p.act = a.act;
+    p.out_f32 = a.out.f32 ? 1 : 0;
+    const long long oCs = a.out.Cs;
+    const long long Wfull = a.out.W;
+    if (!a.head) {
+        const long long base_off = ((long long)a.phy * Wfull + a.phx) * oCs + a.out.c_off;
+        p.out = a.out.f32 ? (void*)((float*)a.out.base + base_off) : (void*)(a.out.base + base_off);
+        p.out_sn = (long long)a.out.H * Wfull * oCs;
+        p.out_sy = (long long)a.osy * Wfull * oCs;
+        p.out_sx = (long long)a.osx * oCs;
+    }
+    if (a.res) {
+        p.res = a.res->ptr();
+        p.res_sn = (long long)a.res->H * a.res->W * a.res->Cs;
+        p.res_sy = (long long)a.res->W * a.res->Cs;
+        p.res_sx = a.res->Cs;
+    }
+    p.scale = a.scale + a.ch_off;
+    p.shift = a.shift + a.ch_off;
+    p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = nullptr; p.head_B = a.head_B; p.head_T = a.head_T;
+    if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
+    for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; }
+    const int total = m_tiles * p.n_tiles;
+    op.grid = std::min(total, ctx->num_sms);
+    op.flops = 2.0 * a.macs_per_pixel * (double)a.Wl * a.Hl * a.in.N;
+    pl->ops.push_back(op);
+    return W2L_OK;
+}
+
+// Emit the launches of one block (conv / convT) of a spec table.
+static int emit_block(w2l_ctx* ctx, Plan* pl, int net, int li, const Layer& L, const Act& in, const Act& out,
+                      const Act* res, bool head = false, int head_B = 1, int head_T = 1) {
+    const NetW& nw = ctx->nets[net];
+    const LayerW& lw = nw.layers[li];
+    ConvArgs a;
+    a.in = in; a.out = out; a.res = res;
+    a.scale = lw.scale; a.shift = lw.shift;
+    a.act = (L.kind == W2L_BLOCK_CONV_LRELU) ? ACT_LRELU : (L.kind == W2L_BLOCK_CONV_PLAIN ? ACT_NONE : ACT_RELU);
+    a.cout = L.cout;
+    a.head = head; a.head_w = nw.head_w; a.head_b = nw.head_b; a.head_B = head_B; a.head_T = head_T;
+    if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
+        a.name = L.name;
+        a.w = &lw.ph[0];
+        a.sx = L.sw; a.sy = L.sh;
+        a.Hl = out.H; a.Wl = out.W;
+        a.macs_per_pixel = (double)L.cin * L.cout * L.kh * L.kw;
+        return make_conv_op(ctx, pl, a);
+    }
+    if (lw.gemm_convT) {
+        // 1x1 -> kh x kw transposed conv == GEMM with kh*kw*cout output columns landing NHWC-contiguous
+        Act o = out;
+        o.H = 1; o.W = 1; o.Cs = out.Cs * out.H * out.W; o.C = L.cout * L.kh * L.kw;
+        if (out.c_off != 0 || out.C != out.Cs) return fail(W2L_EINVAL, "%s: gemm convT needs a dense output", L.name.c_str());
+        a.name = L.name;
+        a.out = o;
+        a.w = &lw.ph[0];
+        a.Hl = 1; a.Wl = 1;
+        a.cout = L.cout * L.kh * L.kw;
+        a.macs_per_pixel = (double)L.cin * L.cout * L.kh * L.kw;
+        return make_conv_op(ctx, pl, a);
+    }
+    for (size_t i = 0; i < lw.ph.size(); ++i) {
+        const PackedW& w = lw.ph[i];
+        ConvArgs b = a;
+        b.name = L.name + ".ph" + std::to_string(w.py) + std::to_string(w.px);
+        b.w = &w;
+        b.osy = L.sh; b.osx = L.sw; b.phy = w.py; b.phx = w.px;
+        b.Hl = (out.H - w.py + L.sh - 1) / L.sh;
+        b.Wl = (out.W - w.px + L.sw - 1) / L.sw;
+        b.macs_per_pixel = (double)L.cin * L.cout * w.ntaps;
+        CKR(make_conv_op(ctx, pl, b));
+    }
+    return W2L_OK;
+}
+
+static void conv_out_dims(const Layer& L, int H, int W, int* Ho, int* Wo) {
+    if (L.kind == W2L_BLOCK_CONVT_BN_RELU) {
+        *Ho = (H - 1) * L.sh - 2 * L.ph + L.kh + L.out_pad;
+        *Wo = (W - 1) * L.sw - 2 * L.pw + L.kw + L.out_pad;
+    } else {
+        *Ho = (H + 2 * L.ph - L.kh) / L.sh + 1;
+        *Wo = (W + 2 * L.pw - L.kw) / L.sw + 1;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weights
+// ------------------------------------------------------------------------------------------------
+struct TensorRef { const float* p; int64_t n; };
+typedef std::map<std::string, TensorRef> TensorMap;
+
+static int need(const TensorMap& tm, const std::string& name, int64_t numel, const float** out) {
+    auto it = tm.find(name);
+    if (it == tm.end()) return fail(W2L_EINVAL, "missing tensor '%s'", name.c_str());
+    if (it->second.n != numel) return fail(W2L_EINVAL, "tensor '%s' has %lld elements, expected %lld", name.c_str(), (long long)it->second.n, (long long)numel);
+    *out = it->second.p;
+    return W2L_OK;
+}
+
+static int pack_taps(w2l_ctx* ctx, PackedW* pw, const float* src, int cout, int cin, int kh, int kw, bool transposed,
+                     const std::vector<std::pair<int, int>>& rs, int cout_pad_to, cudaStream_t st, uint16_t* dst_override = nullptr) {
+    PackParams pp;
+    memset(&pp, 0, sizeof(pp));
+    pp.src = src;
+    pp.ntaps = (int)rs.size();
+    pp.cout = cout; pp.cin = cin;
+    pp.cin_pad = round_up(cin, 16);
+    pp.cout_pad = round_up(cout, cout_pad_to);
+    if (transposed) { pp.s_ci = (long long)cout * kh * kw; pp.s_co = (long long)kh * kw; }
+    else { pp.s_co = (long long)cin * kh * kw; pp.s_ci = (long long)kh * kw; }
+    pp.s_r = kw; pp.s_s = 1;
+    for (size_t t = 0; t < rs.size(); ++t) { pp.r[t] = (signed char)rs[t].first; pp.s[t] = (signed char)rs[t].second; }
+    const size_t n = (size_t)pp.ntaps * pp.cout_pad * pp.cin_pad;
+    if (dst_override) pp.dst = dst_override;
+    else {
+        void* d = nullptr;
+        CKR(dev_alloc(&d, n * 2));
+        ctx->weight_bytes += n * 2;
+        pp.dst = (uint16_t*)d;
+        pw->w = pp.dst;
+        pw->ntaps = pp.ntaps; pw->cout_pad = pp.cout_pad; pw->cin_pad = pp.cin_pad;
+    }
+    const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+    if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
+    else pack_w_kernel<false><<<blocks, 256, 0, st>>>(pp);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+static void free_layer(LayerW& lw) {
+    for (auto& p : lw.ph) if (p.w) cudaFree(p.w);
+    lw.ph.clear();
+    if (lw.scale) cudaFree(lw.scale);
+    if (lw.shift) cudaFree(lw.shift);
+    lw.scale = lw.shift = nullptr;
+    lw.loaded = false;
+}
+
+// Pack one block's parameters. in_hw1: the block is applied to a 1x1 input (enables the GEMM form of convT).
+static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, const float* bias, const float* gamma,
+                      const float* beta, const float* mean, const float* var, bool in_hw1, cudaStream_t st) {
+    free_layer(*lw);
+    const int pad_to = 16;
+    int reps = 1;
+    if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
+        std::vector<std::pair<int, int>> rs;
+        PackedW pw;
+        for (int r = 0; r < L.kh; ++r)
+            for (int s = 0; s < L.kw; ++s) { rs.push_back({r, s}); pw.dy.push_back((signed char)(r - L.ph)); pw.dx.push_back((signed char)(s - L.pw)); }
+        CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, false, rs, pad_to, st));
+        lw->ph.push_back(pw);
+    } else if (in_hw1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) {
+        // out[n, y, x, co] = sum_ci in[n, ci] * W[ci, co, y, x]  -> GEMM with columns (y, x, co)
+        lw->gemm_convT = true;
+        reps = L.kh * L.kw;
+        PackedW pw;
+        pw.ntaps = 1; pw.cin_pad = round_up(L.cin, 16); pw.cout_pad = round_up(L.cout, pad_to) * reps;
+        pw.dx.push_back(0); pw.dy.push_back(0);
+        void* d = nullptr;
+        const size_t n = (size_t)pw.cout_pad * pw.cin_pad;
+        CKR(dev_alloc(&d, n * 2));
+        ctx->weight_bytes += n * 2;
+        pw.w = (uint16_t*)d;
+        if (L.cout % pad_to != 0) return fail(W2L_EINVAL, "%s: gemm convT needs cout %% 16 == 0", L.name.c_str());
+        for (int r = 0; r < L.kh; ++r)
+            for (int s = 0; s < L.kw; ++s) {
+                std::vector<std::pair<int, int>> rs = {{r, s}};
+                CKR(pack_taps(ctx, nullptr, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st,
+                              pw.w + (size_t)(r * L.kw + s) * L.cout * pw.cin_pad));
+            }
+        lw->ph.push_back(pw);
+    } else {
+        // transposed conv: oy = iy*s - p + r.  Output phase py uses the taps r == (py + p) mod s at input row y + (py + p - r)/s
+        for (int py = 0; py < L.sh; ++py)
+            for (int px = 0; px < L.sw; ++px) {
+                std::vector<std::pair<int, int>> rs;
+                PackedW pw;
+                pw.py = py; pw.px = px;
+                for (int r = 0; r < L.kh; ++r) {
+                    if ((py + L.ph - r) % L.sh != 0) continue;
+                    for (int s = 0; s < L.kw; ++s) {
+                        if ((px + L.pw - s) % L.sw != 0) continue;
+                        rs.push_back({r, s});
+                        pw.dy.push_back((signed char)((py + L.ph - r) / L.sh));
+                        pw.dx.push_back((signed char)((px + L.pw - s) / L.sw));
+                    }
+                }
+                if (rs.empty()) return fail(W2L_EINVAL, "%s: empty transposed-conv phase", L.name.c_str());
+                CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st));
+                lw->ph.push_back(pw);
+            }
+    }
+    const int n_pad = round_up(L.cout, pad_to) * reps;
+    void* sc = nullptr; void* sh = nullptr;
+    CKR(dev_alloc(&sc, (size_t)n_pad * 4));
+    CKR(dev_alloc(&sh, (size_t)n_pad * 4));
+    lw->scale = (float*)sc; lw->shift = (float*)sh; lw->n_scale = n_pad;
+    fold_bn_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, 1e-5f, L.cout, reps, n_pad, lw->scale, lw->shift);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    lw->loaded = true;
+    return W2L_OK;
+}
+
+static int fetch_block_tensors(const TensorMap& tm, const Layer& L, const float** W, const float** b, const float** g,
+                               const float** be, const float** m, const float** v) {
+    const int64_t wn = (int64_t)L.cin * L.cout * L.kh * L.kw;
+    CKR(need(tm, L.name + ".conv_block.0.weight", wn, W));
+    CKR(need(tm, L.name + ".conv_block.0.bias", L.cout, b));
+    *g = *be = *m = *v = nullptr;
+    if (L.kind == W2L_BLOCK_CONV_BN_RELU || L.kind == W2L_BLOCK_CONVT_BN_RELU) {
+        CKR(need(tm, L.name + ".conv_block.1.weight", L.cout, g));
+        CKR(need(tm, L.name + ".conv_block.1.bias", L.cout, be));
+        CKR(need(tm, L.name + ".conv_block.1.running_mean", L.cout, m));
+        CKR(need(tm, L.name + ".conv_block.1.running_var", L.cout, v));
+    }
+    return W2L_OK;
+}
+
+static void drop_plans(w2l_ctx* ctx, int net) {
+    for (auto it = ctx->plans.begin(); it != ctx->plans.end();) {
+        if (it->second->net == net) { free_plan(it->second.get()); it = ctx->plans.erase(it); }
+        else ++it;
+    }
+    ctx->last_plan[net] = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// plans
+// ------------------------------------------------------------------------------------------------
+struct TmpPool {  // two ping-pong temporaries per chain, grown on demand
+    Act slot[2];
+    size_t cap[2] = {0, 0};
+    int next = 0;
+};
+
+static int tmp_act(w2l_ctx* ctx, Plan* pl, TmpPool* tp, Act* a, int N, int H, int W, int C, const uint16_t* avoid) {
+    int s = tp->next;
+    if (tp->slot[s].base != nullptr && tp->slot[s].base == avoid) s ^= 1;
+    const size_t need_b = (size_t)N * H * W * C * 2;
+    if (ctx->keep_all || tp->cap[s] < need_b) {
+        CKR(plan_act(pl, &tp->slot[s], N, H, W, C));
+        tp->cap[s] = need_b;
+    }
+    Act v = tp->slot[s];
+    v.N = N; v.H = H; v.W = W; v.Cs = C; v.c_off = 0; v.C = C;
+    *a = v;
+    tp->next = s ^ 1;
+    return W2L_OK;
+}
+
+static void add_ingest(Plan* pl, const char* name, int src_id, const Act& dst, int B, int C, long long sB, long long sC,
+                       long long sT, int y_off, int Wsrc) {
+    Op op;
+    op.type = OP_INGEST;
+    op.name = name;
+    op.ingest_src = src_id;
+    IngestParams& ip = op.ip;
+    ip.src = nullptr; ip.dst = dst.base;
+    ip.N = dst.N; ip.B = B; ip.C = C; ip.H = dst.H; ip.W = dst.W; ip.Cpad = dst.Cs;
+    ip.sB = sB; ip.sC = sC; ip.sT = sT; ip.y_off = y_off; ip.Wsrc = Wsrc;
+    pl->ops.push_back(op);
+}
+
+// a straight chain of blocks (encoders): ping-pong temporaries, optional final destination
+static int emit_chain(w2l_ctx* ctx, Plan* pl, int net, const std::vector<Layer>& layers, const std::vector<int>& idx,
+                      Act x, TmpPool* tp, const Act* final_dst, Act* result) {
+    for (size_t k = 0; k < idx.size(); ++k) {
+        const Layer& L = layers[idx[k]];
+        int Ho, Wo;
+        conv_out_dims(L, x.H, x.W, &Ho, &Wo);
+        Act out;
+        if (k + 1 == idx.size() && final_dst) {
+            out = *final_dst;
+            if (out.H != Ho || out.W != Wo || out.C != L.cout) return fail(W2L_EINVAL, "%s: destination shape mismatch (%dx%dx%d vs %dx%dx%d)", L.name.c_str(), out.H, out.W, out.C, Ho, Wo, L.cout);
+        } else {
+            CKR(tmp_act(ctx, pl, tp, &out, x.N, Ho, Wo, L.cout, x.base));
+        }
+        CKR(emit_block(ctx, pl, net, idx[k], L, x, out, L.residual ? &x : nullptr));
+        pl->layer_out[idx[k]] = out;
+        x = out;
+    }
+    if (result) *result = x;
+    return W2L_OK;
+}
+
+static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
+    const GeneratorSpec& g = gen_spec();
+    const int N = pl->N, B = pl->B, T = pl->T;
+    Act faceIn, melIn;
+    CKR(plan_act(pl, &faceIn, N, 96, 96, 16));
+    CKR(plan_act(pl, &melIn, N, 80, 16, 16));
+    if (T > 0) {
+        add_ingest(pl, "ingest.mel", 0, melIn, B, 1, (long long)T * 1280, 1280, 1280, 0, 16);
+        add_ingest(pl, "ingest.face", 1, faceIn, B, 6, (long long)6 * T * 9216, (long long)T * 9216, 9216, 0, 96);
+    } else {
+        add_ingest(pl, "ingest.mel", 0, melIn, N, 1, 1280, 1280, 0, 0, 16);
+        add_ingest(pl, "ingest.face", 1, faceIn, N, 6, 6 * 9216, 9216, 0, 0, 96);
+    }
+    // skip-concat buffers D[k]: [decoder output | encoder feature] at resolution hw[k]   (wav2lip.py:108)
+    const int hw[7] = {1, 3, 6, 12, 24, 48, 96};
+    const int dec_c[7] = {512, 512, 512, 384, 256, 128, 64};
+    const int skip_c[7] = {512, 512, 256, 128, 64, 32, 16};
+    Act D[7];
+    for (int k = 0; k < 7; ++k) CKR(plan_act(pl, &D[k], N, hw[k], hw[k], dec_c[k] + skip_c[k]));
+
+    // audio encoder -> (N,1,1,512)
+    Act AE;
+    CKR(plan_act(pl, &AE, N, 1, 1, 512));
+    TmpPool tpa;
+    CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.audio_enc, melIn, &tpa, &AE, nullptr));
+
+    // face encoder: stage i ends in the skip half of D[6-i] and the next stage reads it from there
+    TmpPool tpe;
+    Act x = faceIn;
+    for (int i = 0; i < 7; ++i) {
+        Act dst = D[6 - i].slice(dec_c[6 - i], skip_c[6 - i]);
+        CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.face_enc[i], x, &tpe, &dst, &x));
+    }
+    // decoder
+    TmpPool tpd;
+    x = AE;
+    for (int k = 0; k < 7; ++k) {
+        Act dst = D[k].slice(0, dec_c[k]);
+        CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.face_dec[k], x, &tpd, &dst, nullptr));
+        x = D[k];
+    }
+    // output block with the fused 1x1 + sigmoid head; writes the caller's fp32 tensor
+    const Layer& L = g.layers[g.output_block0];
+    Act none;
+    none.N = N; none.H = 96; none.W = 96; none.Cs = 32; none.C = 32;
+    CKR(emit_block(ctx, pl, W2L_NET_GENERATOR, g.output_block0, L, x, none, nullptr, true, T > 0 ? B : N, T > 0 ? T : 1));
+    return W2L_OK;
+}
+
+static int build_syncnet_plan(w2l_ctx* ctx, Plan* pl) {
+    const SyncnetSpec& s = sync_spec();
+    const int N = pl->N;
+    Act faceIn, melIn, fe, ae;
+    CKR(plan_act(pl, &faceIn, N, 48, 96, 16));
+    CKR(plan_act(pl, &melIn, N, 80, 16, 16));
+    CKR(plan_act(pl, &fe, N, 1, 1, 512, true));
+    CKR(plan_act(pl, &ae, N, 1, 1, 512, true));
+    add_ingest(pl, "ingest.mel", 0, melIn, N, 1, 1280, 1280, 0, 0, 16);
+    add_ingest(pl, "ingest.face", 1, faceIn, N, 15, 15 * 4608, 4608, 0, 0, 96);
+    TmpPool tpf, tpa;
+    CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.face_enc, faceIn, &tpf, &fe, nullptr));
+    CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.audio_enc, melIn, &tpa, &ae, nullptr));
+    for (int which = 0; which < 2; ++which) {
+        Op op;
+        op.type = OP_L2NORM;
+        op.name = which == 0 ? "l2norm.audio" : "l2norm.face";
+        op.aux_in = which == 0 ? ae.base : fe.base;
+        op.aux_rows = N; op.aux_dim = 512; op.aux_out = which;
+        pl->ops.push_back(op);
+    }
+    return W2L_OK;
+}
+
+static int build_disc_plan(w2l_ctx* ctx, Plan* pl) {
+    const DiscSpec& d = disc_spec();
+    const int N = pl->N, B = pl->B, T = pl->T;
+    Act in, feat;
+    CKR(plan_act(pl, &in, N, 48, 96, 16));
+    CKR(plan_act(pl, &feat, N, 1, 1, 512));
+    // (B,3,T,96,96): t-major flatten + rows 48..95   (wav2lip.py:155-161)
+    add_ingest(pl, "ingest.frames", 0, in, B, 3, (long long)3 * T * 9216, (long long)T * 9216, 9216, 48, 96);
+    std::vector<int> idx;
+    for (size_t i = 0; i < d.layers.size(); ++i) idx.push_back((int)i);
+    TmpPool tp;
+    CKR(emit_chain(ctx, pl, W2L_NET_DISC, d.layers, idx, in, &tp, &feat, nullptr));
+    Op op;
+    op.type = OP_DISC_HEAD;
+    op.name = "binary_pred";
+    op.aux_in = feat.base; op.aux_rows = N; op.aux_dim = 512; op.aux_out = 0;
+    pl->ops.push_back(op);
+    return W2L_OK;
+}
+
+static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
+    char key[64];
+    snprintf(key, sizeof(key), "%d:%d:%d:%d", net, B, T, (int)ctx->keep_all);
+    auto it = ctx->plans.find(key);
+    if (it != ctx->plans.end()) { *out = it->second.get(); return W2L_OK; }
+    if (!ctx->nets[net].loaded) return fail(W2L_ESTATE, "weights of net %d not loaded", net);
+    // keep at most a few plans per net alive (activation arenas are large)
+    int count = 0;
+    for (auto& kv : ctx->plans) if (kv.second->net == net) ++count;
+    if (count >= 4) drop_plans(ctx, net);
+    std::unique_ptr<Plan> pl(new Plan());
+    pl->net = net; pl->B = B; pl->T = T;
+    pl->N = (net == W2L_NET_SYNCNET) ? B : (T > 0 ? B * T : B);
+    int r = W2L_OK;
+    if (net == W2L_NET_GENERATOR) r = build_generator_plan(ctx, pl.get());
+    else if (net == W2L_NET_SYNCNET) r = build_syncnet_plan(ctx, pl.get());
+    else r = build_disc_plan(ctx, pl.get());
+    if (r != W2L_OK) { free_plan(pl.get()); return r; }
+    *out = pl.get();
+    ctx->plans[key] = std::move(pl);
+    return W2L_OK;
+}
+
+static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, void* out0, void* out1, cudaStream_t st) {
+    for (Op& op : pl->ops) {
+        switch (op.type) {
+            case OP_INGEST: {
+                IngestParams ip = op.ip;
+                ip.src = (const float*)(op.ingest_src == 0 ? in0 : in1);
+                const long long total = (long long)ip.N * ip.H * ip.W;
+                const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+                if (ctx->bf16) ingest_kernel<true><<<blocks, 256, 0, st>>>(ip);
+                else ingest_kernel<false><<<blocks, 256, 0, st>>>(ip);
+                ctx->launches++;
+                break;
+            }
+            case OP_CONV: {
+                if (op.head) op.cp.head_out = (float*)out0;
+                CKR(launch_conv(ctx, op, st));
+                break;
+            }
+            case OP_L2NORM: {
+                float* o = (float*)(op.aux_out == 0 ? out0 : out1);
+                l2norm_kernel<<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const float*)op.aux_in, o, op.aux_rows, op.aux_dim);
+                ctx->launches++;
+                break;
+            }
+            case OP_DISC_HEAD: {
+                const NetW& nw = ctx->nets[W2L_NET_DISC];
+                if (ctx->bf16) disc_head_kernel<true><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim);
+                else disc_head_kernel<false><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim);
+                ctx->launches++;
+                break;
+            }
+        }
+    }
+    CK(cudaGetLastError());
+    ctx->last_plan[pl->net] = pl;
+    return W2L_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// mel tables (host, double precision) — librosa 0.7.0 filters.mel(16000, 800, 80, 55, 7600), Slaney
+// ------------------------------------------------------------------------------------------------
+static double hz_to_mel(double f) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return f >= min_log_hz ? min_log_mel + std::log(f / min_log_hz) / logstep : f / f_sp;
+}
+static double mel_to_hz(double m) {
+    const double f_sp = 200.0 / 3.0, min_log_hz = 1000.0, min_log_mel = min_log_hz / f_sp, logstep = std::log(6.4) / 27.0;
+    return m >= min_log_mel ? min_log_hz * std::exp(logstep * (m - min_log_mel)) : f_sp * m;
+}
+static void build_mel_basis(std::vector<float>* dense) {
+    const int nm = MEL_BANDS, nb = MEL_BINS;
+    dense->assign((size_t)nm * nb, 0.0f);
+    std::vector<double> mel_f(nm + 2);
+    const double m0 = hz_to_mel(55.0), m1 = hz_to_mel(7600.0);
+    const double step = (m1 - m0) / (nm + 1);
+    for (int i = 0; i < nm + 2; ++i) mel_f[i] = mel_to_hz(i == nm + 1 ? m1 : m0 + i * step);
+    for (int i = 0; i < nm; ++i) {
+        const double fd0 = mel_f[i + 1] - mel_f[i], fd1 = mel_f[i + 2] - mel_f[i + 1];
+        const double enorm = 2.0 / (mel_f[i + 2] - mel_f[i]);
+        for (int k = 0; k < nb; ++k) {
+            const double f = 8000.0 * k / (nb - 1);
+            const double lower = -(mel_f[i] - f) / fd0, upper = (mel_f[i + 2] - f) / fd1;
+            const float w32 = (float)std::max(0.0, std::min(lower, upper));
+            (*dense)[(size_t)i * nb + k] = (float)((double)w32 * enorm);
+        }
+    }
+}
+
+static int init_mel_tables(w2l_ctx* ctx) {
+    std::vector<double2> tw(MEL_NFFT);
+    for (int m = 0; m < MEL_NFFT; ++m) {
+        // exact octant symmetry is not needed; long double keeps the table at double round-off
+        const long double a = -2.0L * 3.141592653589793238462643383279502884L * m / MEL_NFFT;
+        tw[m] = make_double2((double)cosl(a), (double)sinl(a));
+    }
+    std::vector<float> dense;
+    build_mel_basis(&dense);
+    std::vector<float> vals;
+    std::vector<int> off(MEL_BANDS), start(MEL_BANDS), len(MEL_BANDS);
+    for (int i = 0; i < MEL_BANDS; ++i) {
+        int a = -1, b = -1;
+        for (int k = 0; k < MEL_BINS; ++k)
+            if (dense[(size_t)i * MEL_BINS + k] != 0.0f) { if (a < 0) a = k; b = k; }
+        off[i] = (int)vals.size();
+        start[i] = a < 0 ? 0 : a;
+        len[i] = a < 0 ? 0 : b - a + 1;
+        for (int k = 0; k < len[i]; ++k) vals.push_back(dense[(size_t)i * MEL_BINS + start[i] + k]);
+    }
+    void* p;
+    CKR(dev_alloc(&p, tw.size() * sizeof(double2))); ctx->mel_tw = (double2*)p;
+    CKR(dev_alloc(&p, vals.size() * 4)); ctx->mel_bvals = (float*)p;
+    CKR(dev_alloc(&p, MEL_BANDS * 4)); ctx->mel_boff = (int*)p;
+    CKR(dev_alloc(&p, MEL_BANDS * 4)); ctx->mel_bstart = (int*)p;
+    CKR(dev_alloc(&p, MEL_BANDS * 4)); ctx->mel_blen = (int*)p;
+    CK(cudaMemcpy(ctx->mel_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mel_bvals, vals.data(), vals.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mel_boff, off.data(), MEL_BANDS * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mel_bstart, start.data(), MEL_BANDS * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ctx->mel_blen, len.data(), MEL_BANDS * 4, cudaMemcpyHostToDevice));
+    CK(cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMelSmemBytes));
+    return W2L_OK;
+}
+
+static int ensure_stage(w2l_ctx* ctx, int i, size_t bytes) {
+    if (ctx->stage_bytes[i] >= bytes) return W2L_OK;
+    if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    ctx->stage[i] = nullptr; ctx->stage_bytes[i] = 0;
+    CKR(dev_alloc(&ctx->stage[i], bytes));
+    ctx->stage_bytes[i] = bytes;
+    return W2L_OK;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ------------------------------------------------------------------------------------------------
+// C-ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+int w2l_abi_version(void) { return W2L_ABI_VERSION; }
+const char* w2l_last_error(void) { return g_err.c_str(); }
+
+int w2l_net_num_layers(int net) {
+    const std::vector<Layer>* L = net_layers(net);
+    return L ? (int)L->size() : fail(W2L_EINVAL, "unknown net %d", net);
+}
+
+int w2l_net_layer_info(int net, int index, w2l_layer_info* out) {
+    const std::vector<Layer>* Ls = net_layers(net);
+    if (!Ls || !out || index < 0 || index >= (int)Ls->size()) return fail(W2L_EINVAL, "bad net/index %d/%d", net, index);
+    const Layer& L = (*Ls)[index];
+    memset(out, 0, sizeof(*out));
+    snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
+    out->kind = L.kind; out->cin = L.cin; out->cout = L.cout; out->kh = L.kh; out->kw = L.kw;
+    out->sh = L.sh; out->sw = L.sw; out->ph = L.ph; out->pw = L.pw; out->out_pad = L.out_pad; out->residual = L.residual ? 1 : 0;
+    return W2L_OK;
+}
+
+/* product's own mel filterbank, dense (80 x 401) fp32, host memory — for the parity tests */
+int w2l_mel_basis_host(float* out) {
+    if (!out) return fail(W2L_EINVAL, "null output");
+    std::vector<float> d;
+    build_mel_basis(&d);
+    memcpy(out, d.data(), d.size() * 4);
+    return W2L_OK;
+}
+
+int w2l_create(int device, int precision, w2l_ctx** out) {
+    if (!out) return fail(W2L_EINVAL, "null out");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(W2L_ENODEV, "no CUDA device (this library has no CPU path)"); }
+    if (device < 0 || device >= ndev) return fail(W2L_EINVAL, "device %d out of range (%d devices)", device, ndev);
+    if (precision != W2L_PREC_F16 && precision != W2L_PREC_BF16) return fail(W2L_EINVAL, "unknown precision %d", precision);
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(W2L_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
+    if (!get_encode_fn()) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled not found in the driver");
+    DeviceGuard g(device);
+    w2l_ctx* ctx = new w2l_ctx();
+    ctx->device = device;
+    ctx->bf16 = precision == W2L_PREC_BF16;
+    ctx->num_sms = prop.multiProcessorCount;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete ctx; return fail(W2L_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    int r = init_mel_tables(ctx);
+    if (r != W2L_OK) { delete ctx; return r; }
+    *out = ctx;
+    return W2L_OK;
+}
+
+int w2l_destroy(w2l_ctx* ctx) {
+    if (!ctx) return W2L_OK;
+    DeviceGuard g(ctx->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : ctx->plans) free_plan(kv.second.get());
+    for (int n = 0; n < 3; ++n) {
+        for (auto& lw : ctx->nets[n].layers) free_layer(lw);
+        if (ctx->nets[n].head_w) cudaFree(ctx->nets[n].head_w);
+        if (ctx->nets[n].head_b) cudaFree(ctx->nets[n].head_b);
+    }
+    for (int i = 0; i < 3; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->mel_tw) cudaFree(ctx->mel_tw);
+    if (ctx->mel_bvals) cudaFree(ctx->mel_bvals);
+    if (ctx->mel_boff) cudaFree(ctx->mel_boff);
+    if (ctx->mel_bstart) cudaFree(ctx->mel_bstart);
+    if (ctx->mel_blen) cudaFree(ctx->mel_blen);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return W2L_OK;
+}
+
+int w2l_set_debug(w2l_ctx* ctx, int keep_all_layer_outputs) {
+    if (!ctx) return fail(W2L_EINVAL, "null ctx");
+    ctx->keep_all = keep_all_layer_outputs != 0;
+    return W2L_OK;
+}
+
+int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* names, const void* const* dev_ptrs,
+                     const int64_t* numels, void* stream) {
+    if (!ctx || !names || !dev_ptrs || !numels) return fail(W2L_EINVAL, "null argument");
+    const std::vector<Layer>* Ls = net_layers(net);
+    if (!Ls) return fail(W2L_EINVAL, "unknown net %d", net);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TensorMap tm;
+    for (int i = 0; i < n_tensors; ++i) {
+        std::string nm = names[i];
+        if (nm.rfind("module.", 0) == 0) nm = nm.substr(7);  // DataParallel-era checkpoints, inference.py:174-175
+        tm[nm] = TensorRef{(const float*)dev_ptrs[i], numels[i]};
+    }
+    drop_plans(ctx, net);
+    NetW& nw = ctx->nets[net];
+    nw.loaded = false;
+    nw.layers.resize(Ls->size());
+    // which blocks see a 1x1 input (GEMM form of the transposed conv): generator decoder stage 1
+    for (size_t i = 0; i < Ls->size(); ++i) {
+        const Layer& L = (*Ls)[i];
+        const float *W, *b, *gm, *be, *m, *v;
+        CKR(fetch_block_tensors(tm, L, &W, &b, &gm, &be, &m, &v));
+        const bool hw1 = (net == W2L_NET_GENERATOR && L.name == "face_decoder_blocks.1.0");
+        CKR(load_layer(ctx, &nw.layers[i], L, W, b, gm, be, m, v, hw1, st));
+    }
+    if (nw.head_w) { cudaFree(nw.head_w); nw.head_w = nullptr; }
+    if (nw.head_b) { cudaFree(nw.head_b); nw.head_b = nullptr; }
+    if (net == W2L_NET_GENERATOR || net == W2L_NET_DISC) {
+        const char* wn = net == W2L_NET_GENERATOR ? "output_block.1.weight" : "binary_pred.0.weight";
+        const char* bn = net == W2L_NET_GENERATOR ? "output_block.1.bias" : "binary_pred.0.bias";
+        const int64_t wcount = net == W2L_NET_GENERATOR ? 96 : 512, bcount = net == W2L_NET_GENERATOR ? 3 : 1;
+        const float *hw, *hb;
+        CKR(need(tm, wn, wcount, &hw));
+        CKR(need(tm, bn, bcount, &hb));
+        void* p;
+        CKR(dev_alloc(&p, wcount * 4)); nw.head_w = (float*)p;
+        CKR(dev_alloc(&p, bcount * 4)); nw.head_b = (float*)p;
+        CK(cudaMemcpyAsync(nw.head_w, hw, wcount * 4, cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(nw.head_b, hb, bcount * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    CK(cudaStreamSynchronize(st));  // the caller may free / mutate the fp32 sources after we return
+    nw.loaded = true;
+    return W2L_OK;
+}
+
+int w2l_generator_forward(w2l_ctx* ctx, const float* mel, const float* face, float* out, int B, int T, void* stream) {
+    if (!ctx || !mel || !face || !out) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || T < 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_GENERATOR, B, T, &pl));
+    return run_plan(ctx, pl, mel, face, out, nullptr, (cudaStream_t)stream);
+}
+
+int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_h, const float* face_h, float* out_h, int B, int T) {
+    if (!ctx || !mel_h || !face_h || !out_h) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || T < 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
+    DeviceGuard g(ctx->device);
+    const size_t N = (size_t)B * (T > 0 ? T : 1);
+    const size_t mb = N * 1280 * 4, fb = N * 6 * 9216 * 4, ob = N * 3 * 9216 * 4;
+    CKR(ensure_stage(ctx, 0, mb));
+    CKR(ensure_stage(ctx, 1, fb));
+    CKR(ensure_stage(ctx, 2, ob));
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_GENERATOR, B, T, &pl));
+    CK(cudaMemcpyAsync(ctx->stage[0], mel_h, mb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->stage[1], face_h, fb, cudaMemcpyHostToDevice, ctx->stream));
+    CKR(run_plan(ctx, pl, ctx->stage[0], ctx->stage[1], ctx->stage[2], nullptr, ctx->stream));
+    CK(cudaMemcpyAsync(out_h, ctx->stage[2], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return W2L_OK;
+}
+
+int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float* a_emb, float* v_emb, int B, void* stream) {
+    if (!ctx || !mel || !face || !a_emb || !v_emb) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0) return fail(W2L_EINVAL, "bad batch %d", B);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_SYNCNET, B, 0, &pl));
+    return run_plan(ctx, pl, mel, face, a_emb, v_emb, (cudaStream_t)stream);
+}
+
+int w2l_disc_forward(w2l_ctx* ctx, const float* frames, float* prob, int B, int T, void* stream) {
+    if (!ctx || !frames || !prob) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || T <= 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_DISC, B, T, &pl));
+    return run_plan(ctx, pl, frames, nullptr, prob, nullptr, (cudaStream_t)stream);
+}
+
+int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float* x, int N, int H, int W,
+                           const float* weight, const float* bias, const float* bn_w, const float* bn_b,
+                           const float* bn_m, const float* bn_v, float* y, void* stream) {
+    if (!ctx || !spec || !x || !weight || !y) return fail(W2L_EINVAL, "null argument");
+    if (N <= 0 || H <= 0 || W <= 0) return fail(W2L_EINVAL, "bad shape");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Layer L;
+    L.name = spec->name[0] ? spec->name : "block";
+    L.kind = spec->kind; L.cin = spec->cin; L.cout = spec->cout; L.kh = spec->kh; L.kw = spec->kw;
+    L.sh = spec->sh; L.sw = spec->sw; L.ph = spec->ph; L.pw = spec->pw; L.out_pad = spec->out_pad; L.residual = spec->residual != 0;
+    if (L.cout % 16 != 0) return fail(W2L_EINVAL, "cout must be a multiple of 16");
+    if (L.kh * L.kw > kMaxTaps) return fail(W2L_EINVAL, "kernel too large");
+    int Ho, Wo;
+    conv_out_dims(L, H, W, &Ho, &Wo);
+    if (Ho <= 0 || Wo <= 0) return fail(W2L_EINVAL, "empty output");
+    if (L.residual && (L.cin != L.cout || Ho != H || Wo != W)) return fail(W2L_EINVAL, "residual needs same shape");
+    // a private one-block "network" in slot 3 semantics: reuse the machinery with a scratch NetW
+    NetW saved = ctx->nets[W2L_NET_DISC];  // borrow a slot; restored below
+    NetW scratch;
+    scratch.layers.resize(1);
+    int r = load_layer(ctx, &scratch.layers[0], L, weight, bias, bn_w, bn_b, bn_m, bn_v, H == 1 && W == 1, st);
+    Plan pl;
+    pl.net = W2L_NET_DISC; pl.N = N; pl.B = N; pl.T = 0;
+    Act in, out;
+    const int cpad = round_up(L.cin, 16);
+    if (r == W2L_OK) r = plan_act(&pl, &in, N, H, W, cpad);
+    if (r == W2L_OK) r = plan_act(&pl, &out, N, Ho, Wo, L.cout);
+    if (r == W2L_OK) {
+        add_ingest(&pl, "ingest.x", 0, in, N, L.cin, (long long)L.cin * H * W, (long long)H * W, 0, 0, W);
+        ctx->nets[W2L_NET_DISC] = scratch;
+        r = emit_block(ctx, &pl, W2L_NET_DISC, 0, L, in, out, L.residual ? &in : nullptr);
+        if (r == W2L_OK) {
+            Plan* lp = ctx->last_plan[W2L_NET_DISC];
+            r = run_plan(ctx, &pl, x, nullptr, nullptr, nullptr, st);
+            ctx->last_plan[W2L_NET_DISC] = lp;
+        }
+        ctx->nets[W2L_NET_DISC] = saved;
+    }
+    if (r == W2L_OK) {
+        const long long total = (long long)N * L.cout * Ho * Wo;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, L.cout, 0);
+        else export_kernel<false><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, L.cout, 0);
+        ctx->launches++;
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) r = fail(W2L_ECUDA, "conv block failed: %s", cudaGetErrorString(e));
+    }
+    free_plan(&pl);
+    free_layer(scratch.layers[0]);
+    return r;
+}
+
+int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y, int* n, int* c, int* h, int* w, void* stream) {
+    if (!ctx || net < 0 || net > 2) return fail(W2L_EINVAL, "bad argument");
+    Plan* pl = ctx->last_plan[net];
+    if (!pl) return fail(W2L_ESTATE, "no forward has run for net %d", net);
+    auto it = pl->layer_out.find(layer);
+    if (it == pl->layer_out.end()) return fail(W2L_EINVAL, "layer %d has no materialised output (fused head?)", layer);
+    const Act& a = it->second;
+    if (n) *n = a.N;
+    if (c) *c = a.C;
+    if (h) *h = a.H;
+    if (w) *w = a.W;
+    if (!y) return W2L_OK;
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)a.N * a.C * a.H * a.W;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    const uint16_t* src = a.f32 ? (const uint16_t*)((const float*)a.base + a.c_off) : a.ptr();
+    if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0);
+    else export_kernel<false><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int64_t w2l_mel_num_frames(int64_t n_samples) { return n_samples < 0 ? 0 : 1 + n_samples / MEL_HOP; }
+
+int w2l_melspectrogram(w2l_ctx* ctx, const float* wav, int64_t n_samples, float* mel, void* stream) {
+    if (!ctx || !wav || !mel) return fail(W2L_EINVAL, "null argument");
+    if (n_samples <= MEL_NFFT / 2) return fail(W2L_EINVAL, "need more than %d samples for reflect padding (got %lld)", MEL_NFFT / 2, (long long)n_samples);
+    DeviceGuard g(ctx->device);
+    MelParams p;
+    p.wav = wav; p.L = n_samples; p.mel = mel; p.F = w2l_mel_num_frames(n_samples);
+    p.tw = ctx->mel_tw; p.bvals = ctx->mel_bvals; p.boff = ctx->mel_boff; p.bstart = ctx->mel_bstart; p.blen = ctx->mel_blen;
+    const long long blocks = (p.F + MEL_FPB - 1) / MEL_FPB;
+    mel_kernel<<<(unsigned)blocks, MEL_FPB * MEL_TPF, kMelSmemBytes, (cudaStream_t)stream>>>(p);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_h, int64_t n_samples, float* mel_h) {
+    if (!ctx || !wav_h || !mel_h) return fail(W2L_EINVAL, "null argument");
+    if (n_samples <= MEL_NFFT / 2) return fail(W2L_EINVAL, "need more than %d samples for reflect padding (got %lld)", MEL_NFFT / 2, (long long)n_samples);
+    DeviceGuard g(ctx->device);
+    const int64_t F = w2l_mel_num_frames(n_samples);
+    CKR(ensure_stage(ctx, 0, (size_t)n_samples * 4));
+    CKR(ensure_stage(ctx, 2, (size_t)F * MEL_BANDS * 4));
+    CK(cudaMemcpyAsync(ctx->stage[0], wav_h, (size_t)n_samples * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CKR(w2l_melspectrogram(ctx, (const float*)ctx->stage[0], n_samples, (float*)ctx->stage[2], ctx->stream));
+    CK(cudaMemcpyAsync(mel_h, ctx->stage[2], (size_t)F * MEL_BANDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return W2L_OK;
+}
+
+int64_t w2l_launch_count(const w2l_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int64_t w2l_device_bytes(const w2l_ctx* ctx) {
+    if (!ctx) return 0;
+    size_t b = ctx->weight_bytes;
+    for (auto& kv : ctx->plans) b += kv.second->bytes;
+    for (int i = 0; i < 3; ++i) b += ctx->stage_bytes[i];
+    return (int64_t)b;
+}
+
+int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out, char (*names_out)[64], void* stream) {
+    if (!ctx || net < 0 || net > 2 || iters <= 0) return fail(W2L_EINVAL, "bad argument");
+    Plan* pl = ctx->last_plan[net];
+    if (!pl) return fail(W2L_ESTATE, "no forward has run for net %d", net);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int k = 0;
+    for (Op& op : pl->ops) {
+        if (op.type != OP_CONV || k >= cap) continue;
+        if (op.head && op.cp.head_out == nullptr) continue;
+        CKR(launch_conv(ctx, op, st));  // warm
+        CK(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st));
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_out) ms_out[k] = ms / iters;
+        if (flop_out) flop_out[k] = op.flops;
+        if (names_out) snprintf(names_out[k], 64, "%s", op.name.c_str());
+        ++k;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,29 @@
+"""Mirror of models.SyncNet_color (/root/reference/models/syncnet.py:7-66)."""
+import ctypes as C
+
+import torch
+
+from ._bridge import lib as _lib
+from ._net import NativeNet, build_tree
+
+
+class SyncNet_color(NativeNet):
+    """forward(audio (B,1,80,16), face (B,15,48,96)) -> (audio_embedding, face_embedding), each (B,512),
+    L2-normalised (syncnet.py:59-66)."""
+    NET = _lib.NET_SYNCNET
+
+    def __init__(self):
+        super().__init__()
+        build_tree(self, self.NET)  # face_encoder, audio_encoder
+
+    def forward(self, audio_sequences, face_sequences):
+        ctx = self._ensure(face_sequences)
+        mel, face = self._in(audio_sequences), self._in(face_sequences)
+        B = face.shape[0]
+        if tuple(mel.shape) != (B, 1, 80, 16) or tuple(face.shape[1:]) != (15, 48, 96):
+            raise ValueError(f"expected (B,1,80,16) and (B,15,48,96), got {tuple(mel.shape)} and {tuple(face.shape)}")
+        a = torch.empty((B, 512), device=face.device, dtype=torch.float32)
+        v = torch.empty((B, 512), device=face.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(face.device).cuda_stream
+        _lib.check(ctx.lib.w2l_syncnet_forward(ctx.h, self._p(mel), self._p(face), self._p(a), self._p(v), B, C.c_void_p(stream)))
+        return a, v

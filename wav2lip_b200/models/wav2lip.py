@@ -1,0 +1,75 @@
+"""Mirrors of models.Wav2Lip and models.Wav2Lip_disc_qual (/root/reference/models/wav2lip.py).
+
+Same class names, zero-arg constructors, forward signatures and state_dict keys; the forward
+pass is ONE call into libw2l.so (w2l_generator_forward / w2l_disc_forward)."""
+import ctypes as C
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from ._bridge import lib as _lib
+from ._net import NativeNet, build_tree
+
+
+class Wav2Lip(NativeNet):
+    """wav2lip.py:8-125.  forward(audio_sequences, face_sequences): audio first.
+       4-D: (N,1,80,16), (N,6,96,96) -> (N,3,96,96); 5-D: (B,T,1,80,16), (B,6,T,96,96) -> (B,3,T,96,96)."""
+    NET = _lib.NET_GENERATOR
+
+    def __init__(self):
+        super().__init__()
+        build_tree(self, self.NET)  # face_encoder_blocks, audio_encoder, face_decoder_blocks, output_block.0
+        # wav2lip.py:83-85: output_block = Sequential(Conv2d(80,32,3,1,1), nn.Conv2d(32,3,1,1,0), Sigmoid)
+        self.output_block.add_module("1", nn.Conv2d(32, 3, kernel_size=1, stride=1, padding=0))
+        self.output_block.add_module("2", nn.Sigmoid())
+
+    def forward(self, audio_sequences, face_sequences):
+        ctx = self._ensure(face_sequences)
+        mel, face = self._in(audio_sequences), self._in(face_sequences)
+        if face.dim() > 4:  # wav2lip.py:91-94
+            B, _, T, H, W = face.shape
+            if tuple(mel.shape) != (B, T, 1, 80, 16) or face.shape[1] != 6 or (H, W) != (96, 96):
+                raise ValueError(f"expected (B,T,1,80,16) and (B,6,T,96,96), got {tuple(mel.shape)} and {tuple(face.shape)}")
+            out = torch.empty((B, 3, T, 96, 96), device=face.device, dtype=torch.float32)
+        else:
+            B, T = face.shape[0], 0
+            if tuple(mel.shape) != (B, 1, 80, 16) or tuple(face.shape[1:]) != (6, 96, 96):
+                raise ValueError(f"expected (N,1,80,16) and (N,6,96,96), got {tuple(mel.shape)} and {tuple(face.shape)}")
+            out = torch.empty((B, 3, 96, 96), device=face.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(face.device).cuda_stream
+        _lib.check(ctx.lib.w2l_generator_forward(ctx.h, self._p(mel), self._p(face), self._p(out), B, T, C.c_void_p(stream)))
+        return out
+
+
+class Wav2Lip_disc_qual(NativeNet):
+    """wav2lip.py:127-184.  forward((B,3,T,96,96)) -> (B*T, 1), rows t-major."""
+    NET = _lib.NET_DISC
+
+    def __init__(self):
+        super().__init__()
+        build_tree(self, self.NET)
+        self.binary_pred = nn.Sequential(nn.Conv2d(512, 1, kernel_size=1, stride=1, padding=0), nn.Sigmoid())
+        self.label_noise = .0
+
+    def get_lower_half(self, face_sequences):
+        return face_sequences[:, :, face_sequences.size(2) // 2:]
+
+    def to_2d(self, face_sequences):
+        return torch.cat([face_sequences[:, :, i] for i in range(face_sequences.size(2))], dim=0)
+
+    def forward(self, face_sequences):
+        ctx = self._ensure(face_sequences)
+        x = self._in(face_sequences)
+        if x.dim() != 5 or x.shape[1] != 3 or tuple(x.shape[3:]) != (96, 96):
+            raise ValueError(f"expected (B,3,T,96,96), got {tuple(x.shape)}")
+        B, T = x.shape[0], x.shape[2]
+        out = torch.empty((B * T, 1), device=x.device, dtype=torch.float32)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        _lib.check(ctx.lib.w2l_disc_forward(ctx.h, self._p(x), self._p(out), B, T, C.c_void_p(stream)))
+        return out
+
+    def perceptual_forward(self, false_face_sequences):
+        # wav2lip.py:163-174: BCE(pred, 1) on the device the input lives on
+        pred = self.forward(false_face_sequences)
+        return F.binary_cross_entropy(pred, torch.ones_like(pred))
