@@ -1,0 +1,311 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the hot path on B200 (one JSON line on stdout, rank 0).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): 96x96 face-crops/sec through Wav2Lip.forward, B=128, T=5, mel 80x16.
+One step = one 5-D generator call `Wav2Lip(indiv_mels (128,5,1,80,16), x (128,6,5,96,96))` = 640 crops
+per GPU, eval mode, synthetic seeded inputs, seeded random weights (the reference's default-init
+statistics with randomised BatchNorm).  Weak scaling: every rank runs its own 640-crop batch; there is
+no data-path collective (eval-mode forward has no cross-sample op), torch.distributed carries only the
+barrier and the max-over-ranks time.
+
+  value      crops/s with the inputs resident in HBM, CUDA-event time on the launching stream,
+             barrier + synchronize on both sides of EXACTLY K steps, max over ranks.
+  e2e        the same metric through the C-ABI host entry point (w2l_generator_forward_host): pinned host
+             inputs -> H2D -> forward -> D2H of the (B,3,T,96,96) result, every step.
+  roofline   tensor-core bound: algorithmic FLOPs (7.934 GFLOP/crop) of the conv kernel
+             launches of one step / their summed per-launch CUDA-event durations (measured live, after the
+             timed region), against MEASURED_PEAKS.json's sustained bf16 figure (fp16 runs at the same rate).
+  cpu_baseline  the oracle port (oracle/w2l_oracle.py, torch CPU fp32 = the reference's own arithmetic) on
+             the host cores, N=128 4-D batch (inference.py's default batch), rank 0 at N=1 only.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOP_PER_CROP = 2 * 3966984192  # 3 966.98 MMAC per 96x96 crop
+METRIC = "96x96 face-crops/sec (B=128, T=5, mel 80x16)"
+B_DEFAULT, T_DEFAULT = 128, 5
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"tflops": float(d["bf16_tflops_sustained"]), "tflops_burst": float(d["bf16_tflops"]),
+                "hbm_gbs": float(d["hbm_gbs"]), "src": "measured"}
+    return {"tflops": 1400.0, "tflops_burst": 1590.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for ts, line in self.lines:
+            if ts < t0 - 0.05 or ts > t1 + 0.15:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "samples": len(sm),
+                "reasons": sorted(reasons)}
+
+
+def cpu_baseline_run(n, threads, repeats=1):
+    """The oracle port (the reference's own CPU arithmetic: torch fp32 conv/BN/ReLU) on the host cores."""
+    import torch
+    from oracle import w2l_oracle as O
+    torch.set_num_threads(threads)
+    sd = O.make_state_dict("generator", 0, init="default")
+    mel, face = O.make_generator_inputs(n, 0)
+    with torch.no_grad():
+        O.generator_forward(sd, mel[:2], face[:2])  # warm the thread pool / primitive cache
+        best = None
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.generator_forward(sd, mel, face)
+            dt = time.perf_counter() - t0
+            best = dt if best is None else min(best, dt)
+    return n / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
+    Python and cannot travel to the GPU box) on all host cores, bounded sample per step."""
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    n = 128  # one inference.py batch (inference.py:33) per step: a bounded sample of the 640-crop workload
+    from oracle import w2l_oracle as O
+    torch.set_num_threads(cores)
+    sd = O.make_state_dict("generator", 0, init="default")
+    mel, face = O.make_generator_inputs(n, 0)
+    with torch.no_grad():
+        for _ in range(max(1, min(args.warmup, 2))):
+            O.generator_forward(sd, mel, face)
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            O.generator_forward(sd, mel, face)
+        dt = (time.perf_counter() - t0) / steps
+    v = n / dt
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "crops/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "Wav2Lip.forward eval, B=128 T=5 workload sampled as one N=128 4-D batch per step",
+                   "weights": "seeded random, reference default-init statistics + randomised BatchNorm"},
+        "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
+                         "sample": "N=128 crops per step (4-D call), torch CPU fp32, all host threads"},
+        "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--batch", type=int, default=B_DEFAULT, help="B (windows per GPU per step)")
+    ap.add_argument("--frames", type=int, default=T_DEFAULT, help="T (frames per window)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch table to this file")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import Wav2Lip
+    from wav2lip_b200.parallel import max_over_ranks
+
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    B, T = args.batch, args.frames
+    N = B * T
+
+    # weights + inputs (seeded; every rank its own input seed, identical weights)
+    import ctypes as C
+    torch.manual_seed(0)
+    model = Wav2Lip()  # torch's default Conv2d init == the reference constructor's init statistics
+    gen = torch.Generator().manual_seed(1)
+    for m in model.modules():  # randomise BatchNorm so that the folded scale/shift are not the identity
+        if isinstance(m, torch.nn.BatchNorm2d):
+            m.weight.data = torch.rand(m.weight.shape, generator=gen) + 0.5
+            m.bias.data = torch.randn(m.bias.shape, generator=gen) * 0.1
+            m.running_mean.data = torch.randn(m.running_mean.shape, generator=gen) * 0.1
+            m.running_var.data = torch.rand(m.running_var.shape, generator=gen) + 0.5
+    model = model.to(dev).eval()
+    gin = torch.Generator().manual_seed(100 + rank)
+    mel_h = torch.rand((B, T, 1, 80, 16), generator=gin) * 8 - 4           # normalised mel range [-4, 4]
+    face_h = torch.rand((B, 6, T, 96, 96), generator=gin)                  # BGR/255
+    face_h[:, 0:3, :, 48:, :] = 0.0                                        # masked lower half (inference.py:136-137)
+    mel_h, face_h = mel_h.pin_memory(), face_h.pin_memory()
+    mel_d, face_d = mel_h.to(dev), face_h.to(dev)
+    stream = torch.cuda.current_stream(dev)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            out = model(mel_d, face_d)
+        ctx = model._w2l_ctx
+        barrier()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+            time.sleep(0.25)
+        l0 = ctx.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        t_wall0 = time.time()
+        e0.record(stream)
+        for _ in range(args.steps):
+            out = model(mel_d, face_d)
+        e1.record(stream)
+        torch.cuda.synchronize(dev)
+        t_wall1 = time.time()
+        barrier()
+        launches = ctx.launch_count() - l0
+        ms = e0.elapsed_time(e1)
+        ms = max_over_ranks(ms, dev)
+        clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+        ms_per_step = ms / args.steps
+        value = world * N * args.steps / (ms * 1e-3)
+
+        # ---- e2e: host buffers through the C-ABI host entry point, H2D + forward + D2H every step ----
+        e2e = None
+        if not args.no_e2e:
+            out_h = torch.empty((B, 3, T, 96, 96), dtype=torch.float32).pin_memory()
+
+            def e2e_step():
+                _lib.check(ctx.lib.w2l_generator_forward_host(ctx.h, C.c_void_p(mel_h.data_ptr()), C.c_void_p(face_h.data_ptr()),
+                                                              C.c_void_p(out_h.data_ptr()), B, T))
+            for _ in range(3):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                e2e_step()  # synchronous: returns after the D2H copy has landed
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+            dt = max_over_ranks(dt, dev)
+            barrier()
+            ok = bool(torch.equal(out_h.to(dev), out))
+            e2e = {"value": world * N * args.steps / dt, "unit": "crops/s",
+                   "h2d_bytes_per_step": int(mel_h.numel() * 4 + face_h.numel() * 4),
+                   "d2h_bytes_per_step": int(out_h.numel() * 4), "result_matches_device_path": ok,
+                   "api": "w2l_generator_forward_host (pinned host buffers)", "timer": "host wall clock around synchronous calls"}
+
+        # ---- roofline: per-launch CUDA-event timing of the conv kernel family (after the timed region) ----
+        peaks = load_peaks()
+        prof = ctx.profile_plan(_lib.NET_GENERATOR, iters=3, stream=stream.cuda_stream)
+        conv_ms = sum(m for _, m, _ in prof)
+        conv_flop = sum(f for _, _, f in prof)
+        achieved = conv_flop / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel<BN,BK> (tcgen05 implicit GEMM, all conv launches of one step)",
+                    "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": achieved / peaks["tflops"],
+                    "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['src']}); fp16 operands run at the bf16 rate",
+                    "launches_per_step": len(prof), "conv_ms_per_step_isolated": conv_ms,
+                    "share_of_step": conv_ms / ms_per_step if ms_per_step > 0 else None,
+                    "whole_step_tflops": value / world * FLOP_PER_CROP / 1e12,
+                    "traffic": None}
+        if args.profile_out and rank == 0:
+            with open(args.profile_out, "w") as f:
+                f.write(f"# per-launch CUDA-event times, B={B} T={T} (N={N}), {len(prof)} conv launches, sum {conv_ms:.3f} ms\n")
+                for nm, m, fl in prof:
+                    f.write(f"{nm:36s} {m * 1e3:10.1f} us {fl / m / 1e9 if m > 0 else 0:9.1f} TFLOP/s {100 * m / conv_ms:5.1f}%\n")
+
+    # ---- CPU baseline (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        v, dt = cpu_baseline_run(128, cores)
+        cpu = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
+               "sample": f"one N=128 4-D batch (inference.py batch) = {dt:.2f} s of oracle/w2l_oracle.py (torch CPU fp32, {cores} threads)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic",
+            "config": {"workload": f"BASELINE configs[1] at the metric's B={B}, T={T}: Wav2Lip.forward eval, {N} crops/GPU/step, fp32 NCHW in/out",
+                       "per_gpu_batch": N, "global_batch": N * world, "parallelism": f"replicas x{world}, batch-sharded, no collective",
+                       "weights": "seeded random (reference default-init statistics + randomised BatchNorm)",
+                       "l2": "inputs larger than L2 (141 MB face + activations >> 126 MB), no explicit flush",
+                       "precision": "fp16 operands / fp32 accumulate+epilogue (TF32-class mantissa)"},
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

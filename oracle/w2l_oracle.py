@@ -153,19 +153,27 @@ def disc_layers() -> List[Tuple[str, Row]]:
 # --------------------------------------------------------------------------------------
 # Seeded weights with the reference's key names
 # --------------------------------------------------------------------------------------
-def _block_tensors(prefix: str, row: Row, g: torch.Generator, gain: float) -> Dict[str, torch.Tensor]:
+def _block_tensors(prefix: str, row: Row, g: torch.Generator, gain: float, torch_default: bool = False) -> Dict[str, torch.Tensor]:
     kind, cin, cout, k, _s, _p, _op, _res = row
     kh, kw = _pair(k)
     sd: Dict[str, torch.Tensor] = {}
     fan_in = cin * kh * kw
     if kind == "t":  # nn.ConvTranspose2d weight is (Cin, Cout, kh, kw), conv.py:37
         wshape = (cin, cout, kh, kw)
-        fan_in = cin * kh * kw / 4.0 if kh == 3 else fan_in  # stride-2 convT touches ~K/4 taps per output
+        if torch_default:
+            fan_in = cout * kh * kw  # torch computes fan_in from dim 1 of the stored weight
+        else:
+            fan_in = cin * kh * kw / 4.0 if kh == 3 else fan_in  # stride-2 convT touches ~K/4 taps per output
     else:
         wshape = (cout, cin, kh, kw)
-    bound = gain * math.sqrt(3.0 / fan_in)
+    if torch_default:  # nn.Conv2d.reset_parameters: kaiming_uniform(a=sqrt(5)) -> U(+-1/sqrt(fan_in)) for weight and bias
+        bound = 1.0 / math.sqrt(fan_in)
+        bias_bound = bound
+    else:
+        bound = gain * math.sqrt(3.0 / fan_in)
+        bias_bound = 0.1
     sd[f"{prefix}.conv_block.0.weight"] = (torch.rand(wshape, generator=g) * 2 - 1) * bound
-    sd[f"{prefix}.conv_block.0.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * 0.1
+    sd[f"{prefix}.conv_block.0.bias"] = (torch.rand(cout, generator=g) * 2 - 1) * bias_bound
     if kind != "n":
         sd[f"{prefix}.conv_block.1.weight"] = torch.rand(cout, generator=g) + 0.5          # gamma ~ U(0.5,1.5)
         sd[f"{prefix}.conv_block.1.bias"] = torch.randn(cout, generator=g) * 0.1           # beta  ~ N(0,0.1)
@@ -175,27 +183,35 @@ def _block_tensors(prefix: str, row: Row, g: torch.Generator, gain: float) -> Di
     return sd
 
 
-def make_state_dict(net: str, seed: int = 0, gain: float = 1.0) -> Dict[str, torch.Tensor]:
+def make_state_dict(net: str, seed: int = 0, gain: float = 1.0, init: str = "stress") -> Dict[str, torch.Tensor]:
     """Deterministic fp32 weights (CPU generator) for net in {"generator","syncnet","disc"}.
 
-    BatchNorm affine and running statistics are randomised so that BN folding is actually
-    exercised (a fresh BN is the identity).  `gain` scales conv weights around the
-    variance-preserving value so that activations stay O(1) through ~50 layers.
+    init="stress" (default): variance-preserving conv weights (`gain` around He-uniform) so that
+        activations stay O(1..30) through ~50 layers and the pre-sigmoid logits have std ~2.5 — every
+        layer's rounding error reaches the output.  Much harsher than anything the reference's own
+        initialisation produces.
+    init="default": the statistics of the reference's own constructor (torch's Conv2d default:
+        U(+-1/sqrt(fan_in)) weights and biases) — the "random weights" of BASELINE.json's configs.
+    In both cases BatchNorm affine and running statistics are randomised so that BN folding is
+    actually exercised (a fresh BN is the identity).
     """
+    td = init == "default"
+    if init not in ("stress", "default"):
+        raise ValueError(init)
     g = torch.Generator(device="cpu")
     g.manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
     if net == "generator":
         for prefix, row in generator_layers():
-            sd.update(_block_tensors(prefix, row, g, gain))
+            sd.update(_block_tensors(prefix, row, g, gain, td))
         sd["output_block.1.weight"] = (torch.rand((3, 32, 1, 1), generator=g) * 2 - 1) * math.sqrt(3.0 / 32)
         sd["output_block.1.bias"] = (torch.rand(3, generator=g) * 2 - 1) * 0.1
     elif net == "syncnet":
         for prefix, row in syncnet_layers():
-            sd.update(_block_tensors(prefix, row, g, gain))
+            sd.update(_block_tensors(prefix, row, g, gain, td))
     elif net == "disc":
         for prefix, row in disc_layers():
-            sd.update(_block_tensors(prefix, row, g, gain))
+            sd.update(_block_tensors(prefix, row, g, gain, td))
         sd["binary_pred.0.weight"] = (torch.rand((1, 512, 1, 1), generator=g) * 2 - 1) * math.sqrt(3.0 / 512)
         sd["binary_pred.0.bias"] = (torch.rand(1, generator=g) * 2 - 1) * 0.1
     else:

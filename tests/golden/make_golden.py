@@ -87,6 +87,19 @@ def main():
     out["gen4n3_out"] = y3.numpy()
     for h in hs:
         h.remove()
+    # the reference's own initialisation statistics ("random weights" of BASELINE.json configs[0..1])
+    sdd = O.make_state_dict("generator", seed=0, init="default")
+    gd = Wav2Lip()
+    gd.load_state_dict(sdd, strict=True)
+    gd.eval()
+    lg = {}
+    hd = gd.output_block[1].register_forward_hook(lambda _m, _i, o: lg.__setitem__("l", o.detach().clone()))
+    with torch.no_grad():
+        yd = gd(mel, face)
+    hd.remove()
+    out["gen4_default_out"] = yd.numpy()
+    out["gen4_default_logits"] = lg["l"].numpy()
+    out["gen_default_sd_checksum"] = np.float64(checksum_sd(sdd))
     np.savez_compressed(os.path.join(HERE, "generator.npz"), **out)
 
     # ---------------- syncnet ----------------
