@@ -35,9 +35,10 @@ __device__ __forceinline__ float from16(uint16_t u) {
 
 struct IngestParams {
     const float* src;
-    uint16_t* dst;      // [N][H][W][Cpad]
+    uint16_t* dst;      // [N][H][Wp][Cpad], image column x stored at column x + x_off (zero borders pre-set)
     int N, B;           // n = t*B + b
     int C, H, W, Cpad;
+    int Wp, x_off;      // destination row pitch (pixels) and left border
     long long sB, sC, sT;  // source strides in elements for b, c, t
     int y_off, Wsrc;       // source row offset / row pitch
 };
@@ -52,7 +53,7 @@ __global__ void ingest_kernel(const IngestParams p) {
         const int n = (int)(i / ((long long)p.W * p.H));
         const int b = n % p.B, t = n / p.B;
         const float* s = p.src + b * p.sB + t * p.sT + (long long)(y + p.y_off) * p.Wsrc + x;
-        uint16_t* d = p.dst + i * p.Cpad;
+        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpad;
         for (int c0 = 0; c0 < p.Cpad; c0 += 8) {
             uint16_t h[8];
 #pragma unroll
@@ -103,6 +104,28 @@ __global__ void pack_w_kernel(const PackParams p) {
         const int t = (int)(i / ((long long)p.cin_pad * p.cout_pad));
         float v = 0.0f;
         if (ci < p.cin && co < p.cout) v = p.src[co * p.s_co + ci * p.s_ci + p.r[t] * p.s_r + p.s[t] * p.s_s];
+        p.dst[i] = to16<kBF16>(v);
+    }
+}
+
+// "kw folded into K" packing for the first layers (tiny Cin): dst[r][co][s*Cp + c] = w[co][c][r][s]
+struct PackFoldParams {
+    const float* src;  // (cout, cin, kh, kw)
+    uint16_t* dst;     // [kh][cout_pad][kfold]
+    int kh, kw, cout, cin, cout_pad, kfold, Cp;
+};
+
+template <bool kBF16>
+__global__ void pack_fold_kernel(const PackFoldParams p) {
+    const long long total = (long long)p.kh * p.cout_pad * p.kfold;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(i % p.kfold);
+        const int co = (int)((i / p.kfold) % p.cout_pad);
+        const int r = (int)(i / ((long long)p.kfold * p.cout_pad));
+        const int s = k / p.Cp, c = k % p.Cp;
+        float v = 0.0f;
+        if (s < p.kw && c < p.cin && co < p.cout) v = p.src[(((long long)co * p.cin + c) * p.kh + r) * p.kw + s];
         p.dst[i] = to16<kBF16>(v);
     }
 }

@@ -43,18 +43,9 @@ constexpr int kSmemExtra = 2048;         // 1024 alignment slack + barriers
 
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 
-struct alignas(64) ConvParams {
-    CUtensorMap tmA;  // activations, dims (C, W, H, N), box (BK, bw*sx, bh*sy, bn), elem strides (1,sx,sy,1)
-    CUtensorMap tmB;  // weights, dims (Cin_pad, Cout_pad, taps), box (BK, BN, 1)
-    // M tiling of the logical output grid
-    int tiles_x, tiles_y, tiles_n, n_tiles;
-    int bw, bh, bn;
-    int sx, sy;
-    int Wout, Hout, N;
-    // K loop
-    int ntaps, kc_per_tap;
-    unsigned stage_tx_bytes;  // bytes both TMA loads of one stage deliver
-    // epilogue
+// What the epilogue needs, shared by every conv kernel variant.
+struct EpiParams {
+    int Wout, Hout, N;      // logical output grid of this launch (rows outside are masked)
     int act;
     int out_f32;
     void* out;              // element (n,y,x,c) at out + n*out_sn + y*out_sy + x*out_sx + c  (elements)
@@ -68,6 +59,19 @@ struct alignas(64) ConvParams {
     const float* head_b;
     float* head_out;
     int head_B, head_T;     // n = t*head_B + b ; T=1,B=N for the 4-D call
+};
+
+struct alignas(64) ConvParams {
+    CUtensorMap tmA;  // activations, dims (C, W, H, N), box (BK, bw*sx, bh*sy, bn), elem strides (1,sx,sy,1)
+    CUtensorMap tmB;  // weights, dims (Cin_pad, Cout_pad, taps), box (BK, BN, 1)
+    // M tiling of the logical output grid
+    int tiles_x, tiles_y, tiles_n, n_tiles;
+    int bw, bh, bn;
+    int sx, sy;
+    // K loop
+    int ntaps, kc_per_tap;
+    unsigned stage_tx_bytes;  // bytes both TMA loads of one stage deliver
+    EpiParams ep;
     signed char dx[kMaxTaps];
     signed char dy[kMaxTaps];
 };
@@ -207,6 +211,81 @@ __device__ __forceinline__ float2 unpack2(uint32_t u) {
     }
 }
 
+// One accumulator tile (this thread's row = one output pixel, BN columns) -> epilogue math -> global memory.
+template <int BN, bool kBF16, bool kHead>
+__device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr, bool valid, int n, int y, int x, int nt) {
+    constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld batch
+    const long long o_off = (long long)n * e.out_sn + (long long)y * e.out_sy + (long long)x * e.out_sx;
+    const long long r_off = (long long)n * e.res_sn + (long long)y * e.res_sy + (long long)x * e.res_sx;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += CH) {
+        uint32_t v[CH];
+        tmem_ld16(taddr + c0, v);
+        if constexpr (CH == 32) tmem_ld16(taddr + c0 + 16, v + 16);
+        tmem_ld_wait();
+        if (valid) {
+            const int cg = nt * BN + c0;  // first output channel of this batch
+            float f[CH];
+#pragma unroll
+            for (int j = 0; j < CH; j += 4) {
+                const float4 sc = __ldg(reinterpret_cast<const float4*>(e.scale + cg + j));
+                const float4 sh = __ldg(reinterpret_cast<const float4*>(e.shift + cg + j));
+                f[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x);
+                f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
+                f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
+                f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
+            }
+            if (e.res != nullptr) {
+                const uint4* rp = reinterpret_cast<const uint4*>(
+                    reinterpret_cast<const uint16_t*>(e.res) + r_off + cg);
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) {
+                    const uint4 r = __ldg(rp + j);
+                    const float2 a = unpack2<kBF16>(r.x), b = unpack2<kBF16>(r.y);
+                    const float2 c = unpack2<kBF16>(r.z), d = unpack2<kBF16>(r.w);
+                    f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                    f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                }
+            }
+            if (e.act == ACT_RELU) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.0f);
+            } else if (e.act == ACT_LRELU) {
+#pragma unroll
+                for (int j = 0; j < CH; ++j) f[j] = f[j] > 0.0f ? f[j] : 0.01f * f[j];
+            }
+            if constexpr (kHead) {
+                // wav2lip.py:84-85: Conv2d(32,3,1) + Sigmoid on the fp32 block output still in registers
+                const int hb = n % e.head_B, ht = n / e.head_B;
+                const long long plane = (long long)e.Hout * e.Wout;
+#pragma unroll
+                for (int oc = 0; oc < 3; ++oc) {
+                    float s = __ldg(e.head_b + oc);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) s = fmaf(f[j], __ldg(e.head_w + oc * 32 + j), s);
+                    s = 1.0f / (1.0f + __expf(-s));
+                    e.head_out[(((long long)hb * 3 + oc) * e.head_T + ht) * plane + (long long)y * e.Wout + x] = s;
+                }
+            } else if (e.out_f32) {
+                float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o_off + cg);
+#pragma unroll
+                for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            } else {
+                uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(e.out) + o_off + cg);
+#pragma unroll
+                for (int j = 0; j < CH / 8; ++j) {
+                    uint4 o;
+                    o.x = pack2<kBF16>(f[8 * j + 0], f[8 * j + 1]);
+                    o.y = pack2<kBF16>(f[8 * j + 2], f[8 * j + 3]);
+                    o.z = pack2<kBF16>(f[8 * j + 4], f[8 * j + 5]);
+                    o.w = pack2<kBF16>(f[8 * j + 6], f[8 * j + 7]);
+                    op[j] = o;
+                }
+            }
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
@@ -323,7 +402,6 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         const int px = row % p.bw;
         const int py = (row / p.bw) % p.bh;
         const int pn = row / (p.bw * p.bh);
-        constexpr int CH = (BN >= 32) ? 32 : 16;  // columns per tcgen05.ld batch
         int it = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
@@ -336,80 +414,12 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const int x = tx * p.bw + px;
             const int y = ty * p.bh + py;
             const int n = tn * p.bn + pn;
-            const bool valid = (row < rows_valid) && (x < p.Wout) && (y < p.Hout) && (n < p.N);
+            const bool valid = (row < rows_valid) && (x < p.ep.Wout) && (y < p.ep.Hout) && (n < p.ep.N);
 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
-            const long long o_off = (long long)n * p.out_sn + (long long)y * p.out_sy + (long long)x * p.out_sx;
-            const long long r_off = (long long)n * p.res_sn + (long long)y * p.res_sy + (long long)x * p.res_sx;
-#pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += CH) {
-                uint32_t v[CH];
-                tmem_ld16(taddr + c0, v);
-                if constexpr (CH == 32) tmem_ld16(taddr + c0 + 16, v + 16);
-                tmem_ld_wait();
-                if (valid) {
-                    const int cg = nt * BN + c0;  // first output channel of this batch
-                    float f[CH];
-#pragma unroll
-                    for (int j = 0; j < CH; j += 4) {
-                        const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cg + j));
-                        const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cg + j));
-                        f[j + 0] = fmaf(__uint_as_float(v[j + 0]), sc.x, sh.x);
-                        f[j + 1] = fmaf(__uint_as_float(v[j + 1]), sc.y, sh.y);
-                        f[j + 2] = fmaf(__uint_as_float(v[j + 2]), sc.z, sh.z);
-                        f[j + 3] = fmaf(__uint_as_float(v[j + 3]), sc.w, sh.w);
-                    }
-                    if (p.res != nullptr) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(
-                            reinterpret_cast<const uint16_t*>(p.res) + r_off + cg);
-#pragma unroll
-                        for (int j = 0; j < CH / 8; ++j) {
-                            const uint4 r = __ldg(rp + j);
-                            const float2 a = unpack2<kBF16>(r.x), b = unpack2<kBF16>(r.y);
-                            const float2 c = unpack2<kBF16>(r.z), d = unpack2<kBF16>(r.w);
-                            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                            f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
-                        }
-                    }
-                    if (p.act == ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = fmaxf(f[j], 0.0f);
-                    } else if (p.act == ACT_LRELU) {
-#pragma unroll
-                        for (int j = 0; j < CH; ++j) f[j] = f[j] > 0.0f ? f[j] : 0.01f * f[j];
-                    }
-                    if constexpr (kHead) {
-                        // wav2lip.py:84-85: Conv2d(32,3,1) + Sigmoid on the fp32 block output still in registers
-                        const int hb = n % p.head_B, ht = n / p.head_B;
-                        const long long plane = (long long)p.Hout * p.Wout;
-#pragma unroll
-                        for (int oc = 0; oc < 3; ++oc) {
-                            float s = __ldg(p.head_b + oc);
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) s = fmaf(f[j], __ldg(p.head_w + oc * 32 + j), s);
-                            s = 1.0f / (1.0f + __expf(-s));
-                            p.head_out[(((long long)hb * 3 + oc) * p.head_T + ht) * plane + (long long)y * p.Wout + x] = s;
-                        }
-                    } else if (p.out_f32) {
-                        float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o_off + cg);
-#pragma unroll
-                        for (int j = 0; j < CH / 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                    } else {
-                        uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<uint16_t*>(p.out) + o_off + cg);
-#pragma unroll
-                        for (int j = 0; j < CH / 8; ++j) {
-                            uint4 o;
-                            o.x = pack2<kBF16>(f[8 * j + 0], f[8 * j + 1]);
-                            o.y = pack2<kBF16>(f[8 * j + 2], f[8 * j + 3]);
-                            o.z = pack2<kBF16>(f[8 * j + 4], f[8 * j + 5]);
-                            o.w = pack2<kBF16>(f[8 * j + 6], f[8 * j + 7]);
-                            op[j] = o;
-                        }
-                    }
-                }
-            }
+            epilogue_tile<BN, kBF16, kHead>(p.ep, taddr, valid, n, y, x, nt);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));

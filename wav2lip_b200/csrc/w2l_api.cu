@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -15,6 +16,7 @@
 
 #include "../../include/w2l.h"
 #include "aux_kernels.cuh"
+#include "conv_halo.cuh"
 #include "conv_tcgen05.cuh"
 #include "mel.cuh"
 #include "netspec.h"
@@ -93,6 +95,9 @@ struct Act {
     int c_off = 0;  // first channel of this view
     int C = 0;      // channels of this view
     bool f32 = false;
+    int Wp = 0;     // row pitch in pixels (0 = W); > W only for the zero-bordered first-layer inputs
+    int x_off = 0;  // left border of those inputs
+    int pitch() const { return Wp ? Wp : W; }
     uint16_t* ptr() const { return base + c_off; }
     Act slice(int off, int c) const { Act a = *this; a.c_off = c_off + off; a.C = c; return a; }
 };
@@ -102,6 +107,9 @@ struct PackedW {
     int ntaps = 0, cout_pad = 0, cin_pad = 0;
     std::vector<signed char> dx, dy;  // input offset of each tap relative to (out * stride)
     int py = 0, px = 0;               // output phase (transposed conv)
+    // "kw folded into K" form for tiny-Cin first layers: one K row = kw taps x Cp channels (zero padded to kfold)
+    bool fold = false;
+    int Cp = 0, kfold = 0, win = 0;   // channel pitch of the input, folded K per filter row, pixels spanned by a window
 };
 
 struct LayerW {
@@ -131,6 +139,9 @@ struct Op {
     bool head = false;
     int grid = 0;
     double flops = 0;  // algorithmic (true MACs*2), not padded
+    bool halo = false;  // conv3x3_halo_kernel instead of conv_igemm_kernel
+    HaloParams hp;
+    int halo_smem = 0;
     // ingest
     IngestParams ip;
     int ingest_src = 0;  // which caller tensor: 0 = mel / frames, 1 = face
@@ -153,6 +164,8 @@ struct w2l_ctx {
     bool bf16 = false;
     int num_sms = 148;
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
+    bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
+    bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};
@@ -192,6 +205,23 @@ static int plan_act(Plan* pl, Act* a, int N, int H, int W, int C, bool f32 = fal
     return W2L_OK;
 }
 
+// Buffer the ingest kernel fills for the first block of a chain. Folded first layers read it through an
+// overlapping-window tensor map: channel pitch Cp, rows padded with pw zero pixels on the left and enough
+// on the right for the last window; the view handed to the conv is (C = kfold, W windows).
+static int plan_input_act(Plan* pl, Act* a, int N, int H, int W, int cin, const LayerW& lw, const Layer& L) {
+    const PackedW& w = lw.ph[0];
+    if (!w.fold) return plan_act(pl, a, N, H, W, ((cin + 15) / 16) * 16);
+    const int Wp = ((W + w.win - 1) + 1) / 2 * 2;
+    void* p = nullptr;
+    const size_t bytes = ((size_t)N * H * Wp * w.Cp + w.kfold) * 2;  // + one window of slack at the very end
+    CKR(plan_alloc(pl, &p, bytes));
+    CK(cudaMemset(p, 0, bytes));
+    a->base = (uint16_t*)p;
+    a->N = N; a->H = H; a->W = W; a->Cs = w.Cp; a->c_off = 0; a->C = w.kfold; a->f32 = false;
+    a->Wp = Wp; a->x_off = L.pw;
+    return W2L_OK;
+}
+
 static void free_plan(Plan* pl) {
     for (void* p : pl->allocs) cudaFree(p);
     pl->allocs.clear();
@@ -222,7 +252,36 @@ static ConvKernelEntry* find_conv_kernel(int BN, int BK, bool bf16, bool head) {
     return nullptr;
 }
 
+typedef void (*HaloKernelFn)(const HaloParams);
+struct HaloKernelEntry { int BN, BK; bool bf16, head; HaloKernelFn fn; bool attr_set; };
+#define W2L_HALO_ENTRY(BN_, BK_)                                                    \
+    {BN_, BK_, false, false, conv_patch_kernel<BN_, BK_, false, false>, false},    \
+    {BN_, BK_, true, false, conv_patch_kernel<BN_, BK_, true, false>, false}
+static HaloKernelEntry g_halo_kernels[] = {
+    W2L_HALO_ENTRY(16, 16), W2L_HALO_ENTRY(16, 32), W2L_HALO_ENTRY(16, 64),
+    W2L_HALO_ENTRY(32, 16), W2L_HALO_ENTRY(32, 32), W2L_HALO_ENTRY(32, 64),
+    W2L_HALO_ENTRY(64, 16), W2L_HALO_ENTRY(64, 32), W2L_HALO_ENTRY(64, 64),
+    {32, 16, false, true, conv_patch_kernel<32, 16, false, true>, false},
+    {32, 16, true, true, conv_patch_kernel<32, 16, true, true>, false},
+};
+static HaloKernelEntry* find_halo_kernel(int BN, int BK, bool bf16, bool head) {
+    for (auto& e : g_halo_kernels)
+        if (e.BN == BN && e.BK == BK && e.bf16 == bf16 && e.head == head) return &e;
+    return nullptr;
+}
+
 static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
+    if (op.halo) {
+        HaloKernelEntry* e = find_halo_kernel(op.BN, op.BK, ctx->bf16, op.head);
+        if (!e) return fail(W2L_EINVAL, "no halo kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
+        if (!e->attr_set) {
+            CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kSmemExtra));
+            e->attr_set = true;
+        }
+        e->fn<<<op.grid, kHaloThreads, op.halo_smem, st>>>(op.hp);
+        ctx->launches++;
+        return W2L_OK;
+    }
     ConvKernelEntry* e = find_conv_kernel(op.BN, op.BK, ctx->bf16, op.head);
     if (!e) return fail(W2L_EINVAL, "no conv kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
     if (!e->attr_set) {
@@ -282,16 +341,140 @@ struct ConvArgs {
     int head_B = 1, head_T = 1;
 };
 
-static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
+static void fill_epi(EpiParams* e, const ConvArgs& a) {
+    memset(e, 0, sizeof(*e));
+    e->Wout = a.Wl; e->Hout = a.Hl; e->N = a.in.N;
+    e->act = a.act;
+    e->out_f32 = a.out.f32 ? 1 : 0;
+    const long long oCs = a.out.Cs;
+    const long long Wfull = a.out.W;
+    if (!a.head) {
+        const long long base_off = ((long long)a.phy * Wfull + a.phx) * oCs + a.out.c_off;
+        e->out = a.out.f32 ? (void*)((float*)a.out.base + base_off) : (void*)(a.out.base + base_off);
+        e->out_sn = (long long)a.out.H * Wfull * oCs;
+        e->out_sy = (long long)a.osy * Wfull * oCs;
+        e->out_sx = (long long)a.osx * oCs;
+    }
+    if (a.res) {
+        e->res = a.res->ptr();
+        e->res_sn = (long long)a.res->H * a.res->W * a.res->Cs;
+        e->res_sy = (long long)a.res->W * a.res->Cs;
+        e->res_sx = a.res->Cs;
+    }
+    e->scale = a.scale + a.ch_off;
+    e->shift = a.shift + a.ch_off;
+    e->head_w = a.head_w; e->head_b = a.head_b; e->head_out = nullptr; e->head_B = a.head_B; e->head_T = a.head_T;
+}
+
+static int encode_act_map(w2l_ctx* ctx, CUtensorMap* tm, const Act& in, int BK, int bx, int by, int bn, int sx, int sy,
+                          const char* name) {
     EncodeTiledFn enc = get_encode_fn();
-    if (!enc) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
+    cuuint64_t strides[3] = {(cuuint64_t)in.Cs * 2, (cuuint64_t)in.pitch() * in.Cs * 2, (cuuint64_t)in.H * in.pitch() * in.Cs * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
+    cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
+    CUresult r = enc(tm, dt, 4, in.ptr(), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(A) failed with %d (dims %d,%d,%d,%d box %d,%d,%d,%d)", name, (int)r,
+                    in.C, in.W, in.H, in.N, BK, bx, by, bn);
+    return W2L_OK;
+}
+
+static int encode_w_map(w2l_ctx* ctx, CUtensorMap* tm, const PackedW& w, int BK, int BN, const char* name) {
+    EncodeTiledFn enc = get_encode_fn();
+    const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)w.ntaps};
+    cuuint64_t strides[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout_pad * 2};
+    cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
+    cuuint32_t es[3] = {1, 1, 1};
+    CUresult r = enc(tm, dt, 3, w.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(B) failed with %d", name, (int)r);
+    return W2L_OK;
+}
+
+// Few-channel stride-1 layers: one input patch per tile + resident weights (conv_halo.cuh)
+struct PatchGeom { int ox, oy, PW, PH, BK, patch_bytes, patch_stride, wbytes; };
+
+static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) {
+    if (!ctx->use_halo) return false;
+    const PackedW& w = *a.w;
+    if (a.sx != 1 || a.sy != 1 || w.ntaps > kHaloMaxTaps) return false;
+    if (a.cout != 16 && a.cout != 32 && a.cout != 64) return false;
+    if (w.cout_pad != a.cout) return false;
+    if (a.head && a.cout != 32) return false;
+    if (a.Wl < kHaloW || a.Hl < kHaloW) return false;
+    const double tiles = (double)((a.Wl + kHaloW - 1) / kHaloW) * ((a.Hl + kHaloH - 1) / kHaloH);
+    if ((double)a.Wl * a.Hl / (tiles * kTileM) < 0.6) return false;
+    int mnx = 127, mxx = -127, mny = 127, mxy = -127;
+    for (int t = 0; t < w.ntaps; ++t) {
+        mnx = std::min(mnx, (int)w.dx[t]); mxx = std::max(mxx, (int)w.dx[t]);
+        mny = std::min(mny, (int)w.dy[t]); mxy = std::max(mxy, (int)w.dy[t]);
+    }
+    g->ox = mnx; g->oy = mny;
+    g->PW = kHaloW + (mxx - mnx); g->PH = kHaloH + (mxy - mny);
+    g->BK = pick_bk(w.cin_pad);
+    g->patch_bytes = g->PW * g->PH * g->BK * 2;
+    g->patch_stride = (g->patch_bytes + 1023) / 1024 * 1024;
+    g->wbytes = w.ntaps * w.cin_pad * a.cout * 2;
+    if (g->PW > 256 || g->PH > 256) return false;
+    if (g->wbytes + 2 * (w.cin_pad / g->BK) * g->patch_stride > kSmemBudget) return false;  // >= 2 stages of a whole tile
+    return true;
+}
+
+static int make_halo_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchGeom& g) {
     Op op;
     op.type = OP_CONV;
-    op.name = a.name;
+    op.name = a.name + (a.w->fold ? " [fold+patch]" : " [patch]");
+    op.halo = true;
+    op.head = a.head;
     const PackedW& w = *a.w;
-    const int BK = pick_bk(w.cin_pad);
+    const int BK = g.BK, BN = a.cout;
+    op.BN = BN; op.BK = BK;
+    HaloParams& h = op.hp;
+    memset(&h, 0, sizeof(h));
+    CKR(encode_act_map(ctx, &h.tmA, a.in, BK, g.PW, g.PH, 1, 1, 1, a.name.c_str()));
+    CKR(encode_w_map(ctx, &h.tmB, w, BK, BN, a.name.c_str()));
+    h.tiles_x = (a.Wl + kHaloW - 1) / kHaloW;
+    h.tiles_y = (a.Hl + kHaloH - 1) / kHaloH;
+    h.kc = w.cin_pad / BK;
+    h.PW = g.PW; h.PH = g.PH; h.ox = g.ox; h.oy = g.oy;
+    h.ntaps = w.ntaps;
+    h.patch_bytes = g.patch_bytes; h.patch_stride = g.patch_stride;
+    for (int t = 0; t < w.ntaps; ++t) h.tap_row[t] = (w.dy[t] - g.oy) * g.PW + (w.dx[t] - g.ox);
+    h.stages = std::min(kHaloMaxStages, (kSmemBudget - g.wbytes) / (h.kc * g.patch_stride));
+    op.halo_smem = g.wbytes + h.stages * h.kc * g.patch_stride + kSmemExtra;
+    fill_epi(&h.ep, a);
+    // constant-bank copies of the folded BatchNorm and the head (plan-build time only)
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.cscale, a.scale + a.ch_off, (size_t)BN * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.cshift, a.shift + a.ch_off, (size_t)BN * 4, cudaMemcpyDeviceToHost));
+    if (a.head) {
+        CK(cudaMemcpy(h.chead_w, a.head_w, 96 * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.chead_b, a.head_b, 3 * 4, cudaMemcpyDeviceToHost));
+    }
+    const long long total = (long long)h.tiles_x * h.tiles_y * a.in.N;
+    op.grid = (int)std::min<long long>(total, ctx->num_sms);
+    op.flops = 2.0 * a.macs_per_pixel * (double)a.Wl * a.Hl * a.in.N;
+    pl->ops.push_back(op);
+    return W2L_OK;
+}
+
+static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
+    if (!get_encode_fn()) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
+    const PackedW& w = *a.w;
     if (a.in.C != w.cin_pad) return fail(W2L_EINVAL, "%s: input view has %d channels, weights packed for %d", a.name.c_str(), a.in.C, w.cin_pad);
     if (a.cout % 16 != 0) return fail(W2L_EINVAL, "%s: cout %d not a multiple of 16", a.name.c_str(), a.cout);
+    PatchGeom geom;
+    if (patch_eligible(ctx, a, &geom)) return make_halo_op(ctx, pl, a, geom);
+    Op op;
+    op.type = OP_CONV;
+    op.name = a.name + (w.fold ? " [fold]" : "");
+    const int BK = pick_bk(w.cin_pad);
     int bw, bh, bn;
     pick_box(a.Wl, a.Hl, a.in.N, a.sx, a.sy, &bw, &bh, &bn);
     const int tiles_x = (a.Wl + bw - 1) / bw, tiles_y = (a.Hl + bh - 1) / bh, tiles_n = (a.in.N + bn - 1) / bn;
@@ -307,54 +490,14 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
 
     ConvParams& p = op.cp;
     memset(&p, 0, sizeof(p));
-    const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
-    const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)a.in.C, (cuuint64_t)a.in.W, (cuuint64_t)a.in.H, (cuuint64_t)a.in.N};
-        cuuint64_t strides[3] = {(cuuint64_t)a.in.Cs * 2, (cuuint64_t)a.in.W * a.in.Cs * 2, (cuuint64_t)a.in.H * a.in.W * a.in.Cs * 2};
-        cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)(bw * a.sx), (cuuint32_t)(bh * a.sy), (cuuint32_t)bn};
-        cuuint32_t es[4] = {1, (cuuint32_t)a.sx, (cuuint32_t)a.sy, 1};
-        CUresult r = enc(&p.tmA, dt, 4, a.in.ptr(), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS)
-            return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(A) failed with %d (dims %d,%d,%d,%d box %d,%d,%d,%d)", a.name.c_str(), (int)r,
-                        a.in.C, a.in.W, a.in.H, a.in.N, BK, bw * a.sx, bh * a.sy, bn);
-    }
-    {
-        cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)w.ntaps};
-        cuuint64_t strides[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout_pad * 2};
-        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
-        cuuint32_t es[3] = {1, 1, 1};
-        CUresult r = enc(&p.tmB, dt, 3, w.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
-                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(B) failed with %d", a.name.c_str(), (int)r);
-    }
+    CKR(encode_act_map(ctx, &p.tmA, a.in, BK, bw * a.sx, bh * a.sy, bn, a.sx, a.sy, a.name.c_str()));
+    CKR(encode_w_map(ctx, &p.tmB, w, BK, BN, a.name.c_str()));
     p.tiles_x = tiles_x; p.tiles_y = tiles_y; p.tiles_n = tiles_n; p.n_tiles = a.cout / BN;
     p.bw = bw; p.bh = bh; p.bn = bn;
     p.sx = a.sx; p.sy = a.sy;
-    p.Wout = a.Wl; p.Hout = a.Hl; p.N = a.in.N;
     p.ntaps = w.ntaps; p.kc_per_tap = w.cin_pad / BK;
     p.stage_tx_bytes = (unsigned)(bw * bh * bn * BK * 2 + BN * BK * 2);
-    p.act = a.act;
-    p.out_f32 = a.out.f32 ? 1 : 0;
-    const long long oCs = a.out.Cs;
-    const long long Wfull = a.out.W;
-    if (!a.head) {
-        const long long base_off = ((long long)a.phy * Wfull + a.phx) * oCs + a.out.c_off;
-        p.out = a.out.f32 ? (void*)((float*)a.out.base + base_off) : (void*)(a.out.base + base_off);
-        p.out_sn = (long long)a.out.H * Wfull * oCs;
-        p.out_sy = (long long)a.osy * Wfull * oCs;
-        p.out_sx = (long long)a.osx * oCs;
-    }
-    if (a.res) {
-        p.res = a.res->ptr();
-        p.res_sn = (long long)a.res->H * a.res->W * a.res->Cs;
-        p.res_sy = (long long)a.res->W * a.res->Cs;
-        p.res_sx = a.res->Cs;
-    }
-    p.scale = a.scale + a.ch_off;
-    p.shift = a.shift + a.ch_off;
-    p.head_w = a.head_w; p.head_b = a.head_b; p.head_out = nullptr; p.head_B = a.head_B; p.head_T = a.head_T;
+    fill_epi(&p.ep, a);
     if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
     for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; }
     const int total = m_tiles * p.n_tiles;
@@ -476,11 +619,35 @@ static void free_layer(LayerW& lw) {
 
 // Pack one block's parameters. in_hw1: the block is applied to a 1x1 input (enables the GEMM form of convT).
 static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, const float* bias, const float* gamma,
-                      const float* beta, const float* mean, const float* var, bool in_hw1, cudaStream_t st) {
+                      const float* beta, const float* mean, const float* var, bool in_hw1, bool first_layer, cudaStream_t st) {
     free_layer(*lw);
     const int pad_to = 16;
     int reps = 1;
-    if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
+    if (first_layer && ctx->use_fold && L.kind != W2L_BLOCK_CONVT_BN_RELU && L.cin <= 16 && L.kw >= 3 && L.sw == 1) {
+        // tiny-Cin first layer: fold the kw horizontal taps into K (one K row per filter row r)
+        PackedW pw;
+        pw.fold = true;
+        pw.Cp = L.cin <= 8 ? 8 : 16;
+        const int raw = L.kw * pw.Cp;
+        pw.kfold = raw <= 32 ? 32 : round_up(raw, 64);
+        pw.win = pw.kfold / pw.Cp;
+        pw.ntaps = L.kh; pw.cin_pad = pw.kfold; pw.cout_pad = round_up(L.cout, pad_to);
+        for (int r = 0; r < L.kh; ++r) { pw.dy.push_back((signed char)(r - L.ph)); pw.dx.push_back(0); }
+        const size_t n = (size_t)pw.ntaps * pw.cout_pad * pw.kfold;
+        void* d = nullptr;
+        CKR(dev_alloc(&d, n * 2));
+        ctx->weight_bytes += n * 2;
+        pw.w = (uint16_t*)d;
+        PackFoldParams fp;
+        fp.src = W; fp.dst = pw.w; fp.kh = L.kh; fp.kw = L.kw; fp.cout = L.cout; fp.cin = L.cin;
+        fp.cout_pad = pw.cout_pad; fp.kfold = pw.kfold; fp.Cp = pw.Cp;
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+        if (ctx->bf16) pack_fold_kernel<true><<<blocks, 256, 0, st>>>(fp);
+        else pack_fold_kernel<false><<<blocks, 256, 0, st>>>(fp);
+        ctx->launches++;
+        CK(cudaGetLastError());
+        lw->ph.push_back(pw);
+    } else if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
         std::vector<std::pair<int, int>> rs;
         PackedW pw;
         for (int r = 0; r < L.kh; ++r)
@@ -596,6 +763,7 @@ static void add_ingest(Plan* pl, const char* name, int src_id, const Act& dst, i
     IngestParams& ip = op.ip;
     ip.src = nullptr; ip.dst = dst.base;
     ip.N = dst.N; ip.B = B; ip.C = C; ip.H = dst.H; ip.W = dst.W; ip.Cpad = dst.Cs;
+    ip.Wp = dst.pitch(); ip.x_off = dst.x_off;
     ip.sB = sB; ip.sC = sC; ip.sT = sT; ip.y_off = y_off; ip.Wsrc = Wsrc;
     pl->ops.push_back(op);
 }
@@ -626,8 +794,9 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     const GeneratorSpec& g = gen_spec();
     const int N = pl->N, B = pl->B, T = pl->T;
     Act faceIn, melIn;
-    CKR(plan_act(pl, &faceIn, N, 96, 96, 16));
-    CKR(plan_act(pl, &melIn, N, 80, 16, 16));
+    const NetW& nw = ctx->nets[W2L_NET_GENERATOR];
+    CKR(plan_input_act(pl, &faceIn, N, 96, 96, 6, nw.layers[g.face_enc[0][0]], g.layers[g.face_enc[0][0]]));
+    CKR(plan_input_act(pl, &melIn, N, 80, 16, 1, nw.layers[g.audio_enc[0]], g.layers[g.audio_enc[0]]));
     if (T > 0) {
         add_ingest(pl, "ingest.mel", 0, melIn, B, 1, (long long)T * 1280, 1280, 1280, 0, 16);
         add_ingest(pl, "ingest.face", 1, faceIn, B, 6, (long long)6 * T * 9216, (long long)T * 9216, 9216, 0, 96);
@@ -675,8 +844,9 @@ static int build_syncnet_plan(w2l_ctx* ctx, Plan* pl) {
     const SyncnetSpec& s = sync_spec();
     const int N = pl->N;
     Act faceIn, melIn, fe, ae;
-    CKR(plan_act(pl, &faceIn, N, 48, 96, 16));
-    CKR(plan_act(pl, &melIn, N, 80, 16, 16));
+    const NetW& nw = ctx->nets[W2L_NET_SYNCNET];
+    CKR(plan_input_act(pl, &faceIn, N, 48, 96, 15, nw.layers[s.face_enc[0]], s.layers[s.face_enc[0]]));
+    CKR(plan_input_act(pl, &melIn, N, 80, 16, 1, nw.layers[s.audio_enc[0]], s.layers[s.audio_enc[0]]));
     CKR(plan_act(pl, &fe, N, 1, 1, 512, true));
     CKR(plan_act(pl, &ae, N, 1, 1, 512, true));
     add_ingest(pl, "ingest.mel", 0, melIn, N, 1, 1280, 1280, 0, 0, 16);
@@ -699,7 +869,7 @@ static int build_disc_plan(w2l_ctx* ctx, Plan* pl) {
     const DiscSpec& d = disc_spec();
     const int N = pl->N, B = pl->B, T = pl->T;
     Act in, feat;
-    CKR(plan_act(pl, &in, N, 48, 96, 16));
+    CKR(plan_input_act(pl, &in, N, 48, 96, 3, ctx->nets[W2L_NET_DISC].layers[0], d.layers[0]));
     CKR(plan_act(pl, &feat, N, 1, 1, 512));
     // (B,3,T,96,96): t-major flatten + rows 48..95   (wav2lip.py:155-161)
     add_ingest(pl, "ingest.frames", 0, in, B, 3, (long long)3 * T * 9216, (long long)T * 9216, 9216, 48, 96);
@@ -752,7 +922,7 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                 break;
             }
             case OP_CONV: {
-                if (op.head) op.cp.head_out = (float*)out0;
+                if (op.head) { op.cp.ep.head_out = (float*)out0; op.hp.ep.head_out = (float*)out0; }
                 CKR(launch_conv(ctx, op, st));
                 break;
             }
@@ -909,6 +1079,20 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     if (e != cudaSuccess) { delete ctx; return fail(W2L_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     int r = init_mel_tables(ctx);
     if (r != W2L_OK) { delete ctx; return r; }
+    {
+        const char* e1 = getenv("W2L_DISABLE_HALO");
+        const char* e2 = getenv("W2L_DISABLE_FOLD");
+        ctx->use_halo = !(e1 && e1[0] == '1');
+        ctx->use_fold = !(e2 && e2[0] == '1');
+        if (ctx->use_fold) {
+            // the folded first layers need a tensor map whose pixel stride (16 B) is smaller than its inner extent
+            // (128 B): probe once that the driver encodes such overlapping windows
+            Act probe;
+            probe.base = (uint16_t*)ctx->mel_tw; probe.N = 2; probe.H = 16; probe.W = 16; probe.Cs = 8; probe.C = 64; probe.Wp = 24;
+            CUtensorMap tm;
+            if (encode_act_map(ctx, &tm, probe, 64, 8, 8, 2, 1, 1, "probe") != W2L_OK) { ctx->use_fold = false; g_err.clear(); }
+        }
+    }
     *out = ctx;
     return W2L_OK;
 }
@@ -963,7 +1147,9 @@ int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* na
         const float *W, *b, *gm, *be, *m, *v;
         CKR(fetch_block_tensors(tm, L, &W, &b, &gm, &be, &m, &v));
         const bool hw1 = (net == W2L_NET_GENERATOR && L.name == "face_decoder_blocks.1.0");
-        CKR(load_layer(ctx, &nw.layers[i], L, W, b, gm, be, m, v, hw1, st));
+        // blocks fed directly by the ingest kernel (caller tensors): the only ones with a tiny Cin
+        const bool first = L.name == "face_encoder_blocks.0.0" || L.name == "audio_encoder.0" || L.name == "face_encoder.0";
+        CKR(load_layer(ctx, &nw.layers[i], L, W, b, gm, be, m, v, hw1, first, st));
     }
     if (nw.head_w) { cudaFree(nw.head_w); nw.head_w = nullptr; }
     if (nw.head_b) { cudaFree(nw.head_b); nw.head_b = nullptr; }
@@ -1048,16 +1234,17 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     conv_out_dims(L, H, W, &Ho, &Wo);
     if (Ho <= 0 || Wo <= 0) return fail(W2L_EINVAL, "empty output");
     if (L.residual && (L.cin != L.cout || Ho != H || Wo != W)) return fail(W2L_EINVAL, "residual needs same shape");
+    const bool saved_fold = ctx->use_fold;
+    if (L.residual) ctx->use_fold = false;  // the residual is read from the block input: keep it in the plain NHWC layout
     // a private one-block "network" in slot 3 semantics: reuse the machinery with a scratch NetW
     NetW saved = ctx->nets[W2L_NET_DISC];  // borrow a slot; restored below
     NetW scratch;
     scratch.layers.resize(1);
-    int r = load_layer(ctx, &scratch.layers[0], L, weight, bias, bn_w, bn_b, bn_m, bn_v, H == 1 && W == 1, st);
+    int r = load_layer(ctx, &scratch.layers[0], L, weight, bias, bn_w, bn_b, bn_m, bn_v, H == 1 && W == 1, true, st);
     Plan pl;
     pl.net = W2L_NET_DISC; pl.N = N; pl.B = N; pl.T = 0;
     Act in, out;
-    const int cpad = round_up(L.cin, 16);
-    if (r == W2L_OK) r = plan_act(&pl, &in, N, H, W, cpad);
+    if (r == W2L_OK) r = plan_input_act(&pl, &in, N, H, W, L.cin, scratch.layers[0], L);
     if (r == W2L_OK) r = plan_act(&pl, &out, N, Ho, Wo, L.cout);
     if (r == W2L_OK) {
         add_ingest(&pl, "ingest.x", 0, in, N, L.cin, (long long)L.cin * H * W, (long long)H * W, 0, 0, W);
@@ -1081,6 +1268,7 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     }
     free_plan(&pl);
     free_layer(scratch.layers[0]);
+    ctx->use_fold = saved_fold;
     return r;
 }
 
@@ -1160,7 +1348,7 @@ int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, d
     int k = 0;
     for (Op& op : pl->ops) {
         if (op.type != OP_CONV || k >= cap) continue;
-        if (op.head && op.cp.head_out == nullptr) continue;
+        if (op.head && op.cp.ep.head_out == nullptr && op.hp.ep.head_out == nullptr) continue;
         CKR(launch_conv(ctx, op, st));  // warm
         CK(cudaEventRecord(e0, st));
         for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st));
