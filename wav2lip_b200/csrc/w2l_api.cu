@@ -165,6 +165,7 @@ struct w2l_ctx {
     int num_sms = 148;
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
     bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
+    bool use_bn256 = true;  // W2L_DISABLE_BN256=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
@@ -242,6 +243,7 @@ static ConvKernelEntry g_conv_kernels[] = {
     W2L_CONV_ENTRY(32, 16), W2L_CONV_ENTRY(32, 32), W2L_CONV_ENTRY(32, 64),
     W2L_CONV_ENTRY(64, 16), W2L_CONV_ENTRY(64, 32), W2L_CONV_ENTRY(64, 64),
     W2L_CONV_ENTRY(128, 16), W2L_CONV_ENTRY(128, 32), W2L_CONV_ENTRY(128, 64),
+    W2L_CONV_ENTRY(256, 64),
     {32, 16, false, true, conv_igemm_kernel<32, 16, false, true>, ConvCfg<32, 16>::kSmemBytes, false},
     {32, 16, true, true, conv_igemm_kernel<32, 16, true, true>, ConvCfg<32, 16>::kSmemBytes, false},
 };
@@ -398,7 +400,7 @@ static int encode_w_map(w2l_ctx* ctx, CUtensorMap* tm, const PackedW& w, int BK,
 }
 
 // Few-channel stride-1 layers: one input patch per tile + resident weights (conv_halo.cuh)
-struct PatchGeom { int ox, oy, PW, PH, BK, patch_bytes, patch_stride, wbytes; };
+struct PatchGeom { int ox, oy, PW, PH, BK, patch_bytes, patch_stride, wbytes, stg_bytes, res_tap; };
 
 static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) {
     if (!ctx->use_halo) return false;
@@ -408,6 +410,7 @@ static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) 
     if (w.cout_pad != a.cout) return false;
     if (a.head && a.cout != 32) return false;
     if (a.Wl < kHaloW || a.Hl < kHaloW) return false;
+    if (a.out.f32) return false;
     const double tiles = (double)((a.Wl + kHaloW - 1) / kHaloW) * ((a.Hl + kHaloH - 1) / kHaloH);
     if ((double)a.Wl * a.Hl / (tiles * kTileM) < 0.6) return false;
     int mnx = 127, mxx = -127, mny = 127, mxy = -127;
@@ -421,8 +424,19 @@ static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) 
     g->patch_bytes = g->PW * g->PH * g->BK * 2;
     g->patch_stride = (g->patch_bytes + 1023) / 1024 * 1024;
     g->wbytes = w.ntaps * w.cin_pad * a.cout * 2;
+    g->stg_bytes = 2 * ((kTileM * a.cout * 2 + 1023) / 1024 * 1024);  // the kernel always carves two staging tiles
     if (g->PW > 256 || g->PH > 256) return false;
-    if (g->wbytes + 2 * (w.cin_pad / g->BK) * g->patch_stride > kSmemBudget) return false;  // >= 2 stages of a whole tile
+    const int need_stages = a.res ? 3 : 2;  // the epilogue holds the patch of a residual block a little longer
+    if (g->wbytes + g->stg_bytes + need_stages * (w.cin_pad / g->BK) * g->patch_stride > kSmemBudget) return false;
+    g->res_tap = -1;
+    if (a.res) {
+        // the patch kernel takes the residual from the input patch in shared memory: it must BE the block input
+        if (a.res->base != a.in.base || a.res->c_off != a.in.c_off || a.res->Cs != a.in.Cs) return false;
+        if (w.cin_pad != a.cout || w.cin_pad != g->BK) return false;
+        for (int t = 0; t < w.ntaps; ++t)
+            if (w.dx[t] == 0 && w.dy[t] == 0) g->res_tap = t;
+        if (g->res_tap < 0) return false;
+    }
     return true;
 }
 
@@ -446,9 +460,29 @@ static int make_halo_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchGe
     h.ntaps = w.ntaps;
     h.patch_bytes = g.patch_bytes; h.patch_stride = g.patch_stride;
     for (int t = 0; t < w.ntaps; ++t) h.tap_row[t] = (w.dy[t] - g.oy) * g.PW + (w.dx[t] - g.ox);
-    h.stages = std::min(kHaloMaxStages, (kSmemBudget - g.wbytes) / (h.kc * g.patch_stride));
-    op.halo_smem = g.wbytes + h.stages * h.kc * g.patch_stride + kSmemExtra;
+    h.stages = std::min(kHaloMaxStages, (kSmemBudget - g.wbytes - g.stg_bytes) / (h.kc * g.patch_stride));
+    op.halo_smem = g.wbytes + h.stages * h.kc * g.patch_stride + g.stg_bytes + kSmemExtra;
+    if (op.halo_smem > kSmemBudget + kSmemExtra || h.stages < 2) return fail(W2L_EINVAL, "%s: patch kernel smem plan %d B / %d stages", a.name.c_str(), op.halo_smem, h.stages);
     fill_epi(&h.ep, a);
+    h.res_row = g.res_tap >= 0 ? h.tap_row[g.res_tap] : -1;
+    h.pair = h.stages >= 4 ? 1 : 0;
+    if (!a.head) {
+        // TMA-store view of the output: the BN-channel slice, with this launch's pixel strides (transposed-conv phases
+        // interleave), box = one 8 x 16 tile; out-of-range pixels of ragged tiles are clipped by the TMA unit
+        EncodeTiledFn enc = get_encode_fn();
+        const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const CUtensorMapSwizzle sw = BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        cuuint64_t dims[4] = {(cuuint64_t)BN, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
+        cuuint64_t strides[3] = {(cuuint64_t)h.ep.out_sx * 2, (cuuint64_t)h.ep.out_sy * 2, (cuuint64_t)h.ep.out_sn * 2};
+        cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        if (a.out.f32) return fail(W2L_EINVAL, "%s: patch kernel stores 16-bit outputs only", a.name.c_str());
+        CUresult r = enc(&h.tmO, dt, 4, h.ep.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(out) failed with %d", a.name.c_str(), (int)r);
+    } else {
+        h.tmO = h.tmA;  // never used by the head variant; keep the descriptor valid for the prefetch
+    }
     // constant-bank copies of the folded BatchNorm and the head (plan-build time only)
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h.cscale, a.scale + a.ch_off, (size_t)BN * 4, cudaMemcpyDeviceToHost));
@@ -482,6 +516,9 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     int BN = 16;
     for (int cand : {128, 64, 32, 16})
         if (a.cout % cand == 0) { BN = cand; break; }
+    // 256-wide tiles halve the A-operand traffic (L2 -> smem and smem -> tensor core) per FLOP; worth it once
+    // there are enough tiles to fill the machine several times over
+    if (ctx->use_bn256 && BK == 64 && a.cout % 256 == 0 && (long long)m_tiles * (a.cout / 256) >= 3LL * ctx->num_sms) BN = 256;
     if (a.head) BN = 32;
     else
         while (BN > 32 && m_tiles * (a.cout / BN) < ctx->num_sms && a.cout % (BN / 2) == 0) BN /= 2;
@@ -1084,6 +1121,8 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         const char* e2 = getenv("W2L_DISABLE_FOLD");
         ctx->use_halo = !(e1 && e1[0] == '1');
         ctx->use_fold = !(e2 && e2[0] == '1');
+        const char* e3 = getenv("W2L_DISABLE_BN256");
+        ctx->use_bn256 = !(e3 && e3[0] == '1');
         if (ctx->use_fold) {
             // the folded first layers need a tensor map whose pixel stride (16 B) is smaller than its inner extent
             // (128 B): probe once that the driver encodes such overlapping windows
