@@ -18,6 +18,7 @@
 #include "aux_kernels.cuh"
 #include "conv_halo.cuh"
 #include "conv_tcgen05.cuh"
+#include "convt_fused.cuh"
 #include "mel.cuh"
 #include "netspec.h"
 
@@ -118,6 +119,7 @@ struct LayerW {
     float* shift = nullptr;
     int n_scale = 0;
     bool gemm_convT = false;
+    bool has_all_taps = false;  // ph.back() holds all 9 taps of a stride-2 transposed conv (fused 4-phase kernel)
     bool loaded = false;
 };
 
@@ -139,9 +141,11 @@ struct Op {
     bool head = false;
     int grid = 0;
     double flops = 0;  // algorithmic (true MACs*2), not padded
-    bool halo = false;  // conv3x3_halo_kernel instead of conv_igemm_kernel
+    bool halo = false;  // conv_patch_kernel instead of conv_igemm_kernel
     HaloParams hp;
     int halo_smem = 0;
+    bool ctf = false;   // convt_fused_kernel
+    ConvTParams tp;
     // ingest
     IngestParams ip;
     int ingest_src = 0;  // which caller tensor: 0 = mel / frames, 1 = face
@@ -166,6 +170,7 @@ struct w2l_ctx {
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
     bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
+    bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
@@ -272,7 +277,27 @@ static HaloKernelEntry* find_halo_kernel(int BN, int BK, bool bf16, bool head) {
     return nullptr;
 }
 
+typedef void (*CtKernelFn)(const ConvTParams);
+struct CtKernelEntry { int BK; bool bf16; CtKernelFn fn; bool attr_set; };
+static CtKernelEntry g_ct_kernels[] = {
+    {32, false, convt_fused_kernel<32, false>, false}, {32, true, convt_fused_kernel<32, true>, false},
+    {64, false, convt_fused_kernel<64, false>, false}, {64, true, convt_fused_kernel<64, true>, false},
+};
+constexpr int kCtSmemMax = 227 * 1024;
+
 static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
+    if (op.ctf) {
+        CtKernelEntry* e = nullptr;
+        for (auto& k : g_ct_kernels) if (k.BK == op.BK && k.bf16 == ctx->bf16) e = &k;
+        if (!e) return fail(W2L_EINVAL, "no fused convT kernel for BK=%d", op.BK);
+        if (!e->attr_set) {
+            CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemMax));
+            e->attr_set = true;
+        }
+        e->fn<<<op.grid, kCtThreads, op.halo_smem, st>>>(op.tp);
+        ctx->launches++;
+        return W2L_OK;
+    }
     if (op.halo) {
         HaloKernelEntry* e = find_halo_kernel(op.BN, op.BK, ctx->bf16, op.head);
         if (!e) return fail(W2L_EINVAL, "no halo kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
@@ -544,6 +569,69 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     return W2L_OK;
 }
 
+// Conv2dTranspose k3 s2 p1 op1 with 64 output channels: all four phases in one launch (convt_fused.cuh)
+static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const LayerW& lw, const Act& in, const Act& out) {
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available");
+    const PackedW& w = lw.ph.back();  // all 9 taps, tap = r*3 + s
+    Op op;
+    op.type = OP_CONV;
+    op.name = L.name + " [fused 4-phase]";
+    op.ctf = true;
+    const int BK = pick_bk(w.cin_pad);
+    op.BK = BK; op.BN = kCtBN;
+    ConvTParams& t = op.tp;
+    memset(&t, 0, sizeof(t));
+    CKR(encode_act_map(ctx, &t.tmA, in, BK, kCtPW, kCtPH, 1, 1, 1, L.name.c_str()));
+    {
+        const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+        cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, 9};
+        cuuint64_t strides[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout_pad * 2};
+        cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)kCtBN, 9};
+        cuuint32_t es[3] = {1, 1, 1};
+        CUresult r = enc(&t.tmB, dt, 3, w.w, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(B9) failed with %d", L.name.c_str(), (int)r);
+        for (int py = 0; py < 2; ++py)
+            for (int px = 0; px < 2; ++px) {
+                uint16_t* base = out.base + ((long long)py * out.W + px) * out.Cs + out.c_off;
+                cuuint64_t od[4] = {(cuuint64_t)kCtBN, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
+                cuuint64_t os[3] = {(cuuint64_t)2 * out.Cs * 2, (cuuint64_t)2 * out.W * out.Cs * 2, (cuuint64_t)out.H * out.W * out.Cs * 2};
+                cuuint32_t ob[4] = {(cuuint32_t)kCtBN, 8, 16, 1};
+                cuuint32_t oe[4] = {1, 1, 1, 1};
+                CUresult r2 = enc(&t.tmO[py * 2 + px], dt, 4, base, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r2 != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(out phase) failed with %d", L.name.c_str(), (int)r2);
+            }
+    }
+    t.tiles_x = (in.W + 7) / 8; t.tiles_y = (in.H + 15) / 16; t.N = in.N;
+    t.kc = w.cin_pad / BK;
+    t.patch_bytes = kCtPW * kCtPH * BK * 2;
+    t.patch_stride = (t.patch_bytes + 1023) / 1024 * 1024;
+    const int stage_bytes = t.patch_stride + 9 * kCtBN * BK * 2;
+    const int fixed = 2 * kTileM * kCtBN * 2 + kSmemExtra;
+    t.stages = std::min(kCtMaxStages, (kCtSmemMax - fixed) / stage_bytes);
+    if (t.stages < 2) return fail(W2L_EINVAL, "%s: fused convT does not fit shared memory", L.name.c_str());
+    op.halo_smem = t.stages * stage_bytes + fixed;
+    t.act = ACT_RELU;
+    for (int r = 0; r < 3; ++r)
+        for (int s2 = 0; s2 < 3; ++s2) {
+            const int py = (r + 1) & 1, px = (s2 + 1) & 1;       // r == (py + pad) mod stride, pad = 1
+            const int dy = (py + 1 - r) / 2, dx = (px + 1 - s2) / 2;
+            t.tap_phase[r * 3 + s2] = py * 2 + px;
+            t.tap_row[r * 3 + s2] = dy * kCtPW + dx;
+        }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(t.cscale, lw.scale, kCtBN * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(t.cshift, lw.shift, kCtBN * 4, cudaMemcpyDeviceToHost));
+    const long long units = (long long)t.tiles_x * t.tiles_y * in.N;
+    op.grid = (int)std::min<long long>(units, ctx->num_sms);
+    op.flops = 2.0 * (double)L.cin * L.cout * 9 * (double)in.W * in.H * in.N;
+    pl->ops.push_back(op);
+    return W2L_OK;
+}
+
 // Emit the launches of one block (conv / convT) of a spec table.
 static int emit_block(w2l_ctx* ctx, Plan* pl, int net, int li, const Layer& L, const Act& in, const Act& out,
                       const Act* res, bool head = false, int head_B = 1, int head_T = 1) {
@@ -576,7 +664,11 @@ static int emit_block(w2l_ctx* ctx, Plan* pl, int net, int li, const Layer& L, c
         a.macs_per_pixel = (double)L.cin * L.cout * L.kh * L.kw;
         return make_conv_op(ctx, pl, a);
     }
-    for (size_t i = 0; i < lw.ph.size(); ++i) {
+    if (lw.has_all_taps && ctx->use_ctfused && in.W >= 8 && in.H >= 8 &&
+        (double)in.W * in.H / ((double)((in.W + 7) / 8) * ((in.H + 15) / 16) * kTileM) >= 0.6 && !out.f32)
+        return make_convt_fused_op(ctx, pl, L, lw, in, out);
+    const size_t nph = lw.ph.size() - (lw.has_all_taps ? 1 : 0);
+    for (size_t i = 0; i < nph; ++i) {
         const PackedW& w = lw.ph[i];
         ConvArgs b = a;
         b.name = L.name + ".ph" + std::to_string(w.py) + std::to_string(w.px);
@@ -652,6 +744,8 @@ static void free_layer(LayerW& lw) {
     if (lw.shift) cudaFree(lw.shift);
     lw.scale = lw.shift = nullptr;
     lw.loaded = false;
+    lw.has_all_taps = false;
+    lw.gemm_convT = false;
 }
 
 // Pack one block's parameters. in_hw1: the block is applied to a 1x1 input (enables the GEMM form of convT).
@@ -731,6 +825,16 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
                 CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st));
                 lw->ph.push_back(pw);
             }
+        if (L.cout == kCtBN && L.kh == 3 && L.kw == 3 && L.sh == 2 && L.sw == 2 && L.ph == 1 && L.pw == 1 && L.out_pad == 1) {
+            // all nine taps in (r, s) order for the fused four-phase kernel
+            std::vector<std::pair<int, int>> rs;
+            PackedW pw;
+            for (int r = 0; r < 3; ++r)
+                for (int s2 = 0; s2 < 3; ++s2) { rs.push_back({r, s2}); pw.dy.push_back(0); pw.dx.push_back(0); }
+            CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st));
+            lw->ph.push_back(pw);
+            lw->has_all_taps = true;
+        }
     }
     const int n_pad = round_up(L.cout, pad_to) * reps;
     void* sc = nullptr; void* sh = nullptr;
@@ -1123,6 +1227,8 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_fold = !(e2 && e2[0] == '1');
         const char* e3 = getenv("W2L_DISABLE_BN256");
         ctx->use_bn256 = !(e3 && e3[0] == '1');
+        const char* e4 = getenv("W2L_DISABLE_CTFUSED");
+        ctx->use_ctfused = !(e4 && e4[0] == '1');
         if (ctx->use_fold) {
             // the folded first layers need a tensor map whose pixel stride (16 B) is smaller than its inner extent
             // (128 B): probe once that the driver encodes such overlapping windows
