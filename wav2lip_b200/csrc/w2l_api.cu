@@ -177,10 +177,12 @@ struct w2l_ctx {
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};
     int64_t launches = 0;
     size_t weight_bytes = 0;
-    // host-buffer entry points
+    // host-buffer entry points: compute stream + copy streams, double-buffered device staging
     cudaStream_t stream = nullptr;
-    void* stage[3] = {nullptr, nullptr, nullptr};
-    size_t stage_bytes[3] = {0, 0, 0};
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
     // mel tables
     double2* mel_tw = nullptr;
     float* mel_bvals = nullptr;
@@ -1217,6 +1219,13 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     ctx->bf16 = precision == W2L_PREC_BF16;
     ctx->num_sms = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
+        e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
+    }
     if (e != cudaSuccess) { delete ctx; return fail(W2L_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     int r = init_mel_tables(ctx);
     if (r != W2L_OK) { delete ctx; return r; }
@@ -1252,7 +1261,10 @@ int w2l_destroy(w2l_ctx* ctx) {
         if (ctx->nets[n].head_w) cudaFree(ctx->nets[n].head_w);
         if (ctx->nets[n].head_b) cudaFree(ctx->nets[n].head_b);
     }
-    for (int i = 0; i < 3; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    for (int i = 0; i < 6; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
+    if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
+    if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]); }
     if (ctx->mel_tw) cudaFree(ctx->mel_tw);
     if (ctx->mel_bvals) cudaFree(ctx->mel_bvals);
     if (ctx->mel_boff) cudaFree(ctx->mel_boff);
@@ -1329,17 +1341,37 @@ int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_h, const float* fa
     if (!ctx || !mel_h || !face_h || !out_h) return fail(W2L_EINVAL, "null argument");
     if (B <= 0 || T < 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
     DeviceGuard g(ctx->device);
-    const size_t N = (size_t)B * (T > 0 ? T : 1);
-    const size_t mb = N * 1280 * 4, fb = N * 6 * 9216 * 4, ob = N * 3 * 9216 * 4;
-    CKR(ensure_stage(ctx, 0, mb));
-    CKR(ensure_stage(ctx, 1, fb));
-    CKR(ensure_stage(ctx, 2, ob));
-    Plan* pl;
-    CKR(get_plan(ctx, W2L_NET_GENERATOR, B, T, &pl));
-    CK(cudaMemcpyAsync(ctx->stage[0], mel_h, mb, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(ctx->stage[1], face_h, fb, cudaMemcpyHostToDevice, ctx->stream));
-    CKR(run_plan(ctx, pl, ctx->stage[0], ctx->stage[1], ctx->stage[2], nullptr, ctx->stream));
-    CK(cudaMemcpyAsync(out_h, ctx->stage[2], ob, cudaMemcpyDeviceToHost, ctx->stream));
+    // The batch is cut along B into up to 4 chunks (whole T-windows, so every chunk is itself a legal call) and
+    // software-pipelined over three streams: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i.
+    const int tt = T > 0 ? T : 1;
+    int nchunks = B >= 64 ? 2 : 1;  // fewer, larger chunks: small batches run the low-resolution layers inefficiently
+    if (const char* ev = getenv("W2L_HOST_CHUNKS")) nchunks = std::max(1, std::min(atoi(ev), B));
+    const int cb = (B + nchunks - 1) / nchunks;
+    const size_t per_b_mel = (size_t)tt * 1280 * 4, per_b_face = (size_t)tt * 6 * 9216 * 4, per_b_out = (size_t)tt * 3 * 9216 * 4;
+    for (int i = 0; i < 2; ++i) {
+        CKR(ensure_stage(ctx, 0 + i, cb * per_b_mel));
+        CKR(ensure_stage(ctx, 2 + i, cb * per_b_face));
+        CKR(ensure_stage(ctx, 4 + i, cb * per_b_out));
+    }
+    int k = 0;
+    for (int b0 = 0; b0 < B; b0 += cb, ++k) {
+        const int bc = std::min(cb, B - b0);
+        const int sl = k & 1;
+        Plan* pl;
+        CKR(get_plan(ctx, W2L_NET_GENERATOR, bc, T, &pl));
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));  // staging_in[sl] free again
+        CK(cudaMemcpyAsync(ctx->stage[0 + sl], (const char*)mel_h + b0 * per_b_mel, bc * per_b_mel, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(ctx->stage[2 + sl], (const char*)face_h + b0 * per_b_face, bc * per_b_face, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));  // staging_out[sl] drained
+        CKR(run_plan(ctx, pl, ctx->stage[0 + sl], ctx->stage[2 + sl], ctx->stage[4 + sl], nullptr, ctx->stream));
+        CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
+        CK(cudaMemcpyAsync((char*)out_h + b0 * per_b_out, ctx->stage[4 + sl], bc * per_b_out, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_out[sl], ctx->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
     CK(cudaStreamSynchronize(ctx->stream));
     return W2L_OK;
 }
@@ -1463,10 +1495,10 @@ int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_h, int64_t n_samples,
     DeviceGuard g(ctx->device);
     const int64_t F = w2l_mel_num_frames(n_samples);
     CKR(ensure_stage(ctx, 0, (size_t)n_samples * 4));
-    CKR(ensure_stage(ctx, 2, (size_t)F * MEL_BANDS * 4));
+    CKR(ensure_stage(ctx, 4, (size_t)F * MEL_BANDS * 4));
     CK(cudaMemcpyAsync(ctx->stage[0], wav_h, (size_t)n_samples * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CKR(w2l_melspectrogram(ctx, (const float*)ctx->stage[0], n_samples, (float*)ctx->stage[2], ctx->stream));
-    CK(cudaMemcpyAsync(mel_h, ctx->stage[2], (size_t)F * MEL_BANDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CKR(w2l_melspectrogram(ctx, (const float*)ctx->stage[0], n_samples, (float*)ctx->stage[4], ctx->stream));
+    CK(cudaMemcpyAsync(mel_h, ctx->stage[4], (size_t)F * MEL_BANDS * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return W2L_OK;
 }
@@ -1477,7 +1509,7 @@ int64_t w2l_device_bytes(const w2l_ctx* ctx) {
     if (!ctx) return 0;
     size_t b = ctx->weight_bytes;
     for (auto& kv : ctx->plans) b += kv.second->bytes;
-    for (int i = 0; i < 3; ++i) b += ctx->stage_bytes[i];
+    for (int i = 0; i < 6; ++i) b += ctx->stage_bytes[i];
     return (int64_t)b;
 }
 
