@@ -14,7 +14,7 @@ from oracle import w2l_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED"]
+FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED", "W2L_DISABLE_MT2"]
 
 
 def _fresh_generator(env):
@@ -100,4 +100,4 @@ def test_launch_counter_and_profile():
     assert len(prof) == per_forward - 2
     total_flop = sum(f for _, _, f in prof)
     assert abs(total_flop / (2 * 2 * 3966984192) - 1) < 0.001  # = 2 crops x 7.934 GFLOP minus the fused 1x1 head
-    assert ctx.device_bytes() > 100e6
+    assert ctx.device_bytes() > 70e6   # >= the packed 16-bit weights (36.3 M params)

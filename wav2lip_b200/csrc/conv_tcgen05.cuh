@@ -179,16 +179,21 @@ __device__ __forceinline__ constexpr uint32_t make_idesc() {
            (static_cast<uint32_t>(kTileM >> 4) << 24);
 }
 
-template <int BN, int BK>
+// MT = number of 128-row M tiles a CTA works on at once (sharing each weight slab): MT = 2 halves the weight
+// traffic per FLOP and alternates MMAs between two independent accumulators.
+template <int BN, int BK, int MT = 1>
 struct ConvCfg {
-    static constexpr int kABytes = kTileM * BK * 2;
+    static constexpr int kATile = kTileM * BK * 2;
+    static constexpr int kABytes = MT * kATile;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kSmemBytes = kStages * kStageBytes + kSmemExtra;
-    static constexpr int kTmemCols = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-    static_assert(2 * BN <= 512, "two accumulator stages must fit TMEM");
+    static constexpr int kAccCols = 2 * MT * BN;
+    static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
+    static constexpr int kThreads = 128 + 128 * MT;  // 4 control warps + 4 epilogue warps per M tile
+    static_assert(kAccCols <= 512, "two accumulator stages must fit TMEM");
     static_assert(kStages >= 2, "need a pipeline");
 };
 
@@ -289,9 +294,9 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr
 // ------------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------------
-template <int BN, int BK, bool kBF16, bool kHead>
-__global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
-    using Cfg = ConvCfg<BN, BK>;
+template <int BN, int BK, bool kBF16, bool kHead, int MT = 1>
+__global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    using Cfg = ConvCfg<BN, BK, MT>;
     constexpr int kStages = Cfg::kStages;
     static_assert(!kHead || BN == 32, "fused head expects the 32-channel output block");
 
@@ -318,7 +323,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(tfull_bar(a), 1);
-            mbar_init(tempty_bar(a), 4);  // one arrive per epilogue warp
+            mbar_init(tempty_bar(a), 4 * MT);  // one arrive per epilogue warp
         }
         fence_barrier_init();
     }
@@ -330,7 +335,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
     const int m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
-    const int total_tiles = m_tiles * p.n_tiles;
+    const int m_units = (m_tiles + MT - 1) / MT;  // a unit = MT consecutive M tiles x one N tile (a tile index past the
+    const int total_tiles = m_units * p.n_tiles;  // end decodes to n >= N: its loads are zero-filled, its rows masked)
     const int k_steps = p.ntaps * p.kc_per_tap;
 
     if (warp == 0) {
@@ -340,22 +346,28 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const int nt = tile % p.n_tiles;
-                const int m = tile / p.n_tiles;
-                const int tx = m % p.tiles_x;
-                const int ty = (m / p.tiles_x) % p.tiles_y;
-                const int tn = m / (p.tiles_x * p.tiles_y);
-                const int x_in0 = tx * p.bw * p.sx;
-                const int y_in0 = ty * p.bh * p.sy;
-                const int n0 = tn * p.bn;
+                const int mu = tile / p.n_tiles;
+                int x_in0[MT], y_in0[MT], n0[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; ++mt) {
+                    const int m = mu * MT + mt;
+                    const int tx = m % p.tiles_x;
+                    const int ty = (m / p.tiles_x) % p.tiles_y;
+                    const int tn = m / (p.tiles_x * p.tiles_y);
+                    x_in0[mt] = tx * p.bw * p.sx;
+                    y_in0[mt] = ty * p.bh * p.sy;
+                    n0[mt] = tn * p.bn;
+                }
                 for (int t = 0; t < p.ntaps; ++t) {
-                    const int cx = x_in0 + p.dx[t];
-                    const int cy = y_in0 + p.dy[t];
                     for (int kc = 0; kc < p.kc_per_tap; ++kc) {
                         mbar_wait(empty_bar(stage), phase ^ 1u);
                         const uint32_t a_dst = smem_base + stage * Cfg::kStageBytes;
                         const uint32_t b_dst = a_dst + Cfg::kABytes;
                         mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
-                        tma_load_4d(a_dst, &p.tmA, full_bar(stage), kc * BK, cx, cy, n0);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            tma_load_4d(a_dst + mt * Cfg::kATile, &p.tmA, full_bar(stage), kc * BK, x_in0[mt] + p.dx[t],
+                                        y_in0[mt] + p.dy[t], n0[mt]);
                         tma_load_3d(b_dst, &p.tmB, full_bar(stage), kc * BK, nt * BN, t);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
@@ -374,18 +386,20 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const uint32_t acc_phase = (it >> 1) & 1u;
             mbar_wait(tempty_bar(acc), acc_phase ^ 1u);  // epilogue has drained this accumulator
             tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BN;
+            const uint32_t tmem_d = tmem_base + acc * (MT * BN);
             for (int ks = 0; ks < k_steps; ++ks) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t a_addr = smem_base + stage * Cfg::kStageBytes;
-                    const uint64_t adesc = make_kmajor_desc<BK>(a_addr);
                     const uint64_t bdesc = make_kmajor_desc<BK>(a_addr + Cfg::kABytes);
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
                         // advance 32 B (16 elements) along K inside the swizzle atom: +2 in the >>4 address field
-                        tc_mma_f16(tmem_d, adesc + 2u * k, bdesc + 2u * k, idesc, (ks | k) != 0 ? 1u : 0u);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt)
+                            tc_mma_f16(tmem_d + mt * BN, make_kmajor_desc<BK>(a_addr + mt * Cfg::kATile) + 2u * k,
+                                       bdesc + 2u * k, idesc, (ks | k) != 0 ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));  // frees the smem stage when these MMAs retire
                     if (ks == k_steps - 1) tc_commit(tfull_bar(acc));
@@ -396,7 +410,8 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
         }
     } else if (warp >= 4) {
         // =============================== epilogue ===============================
-        const int q = warp - 4;            // TMEM lane quarter this warp may access (warp id % 4)
+        const int q = (warp - 4) & 3;      // TMEM lane quarter this warp may access (warp id % 4)
+        const int mt = (warp - 4) >> 2;    // which of the unit's M tiles this epilogue group drains
         const int row = q * 32 + lane;     // GEMM row == pixel index inside the tile box
         const int rows_valid = p.bw * p.bh * p.bn;
         const int px = row % p.bw;
@@ -407,7 +422,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1u;
             const int nt = tile % p.n_tiles;
-            const int m = tile / p.n_tiles;
+            const int m = (tile / p.n_tiles) * MT + mt;
             const int tx = m % p.tiles_x;
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int tn = m / (p.tiles_x * p.tiles_y);
@@ -418,7 +433,7 @@ __global__ void __launch_bounds__(kConvThreads, 1) conv_igemm_kernel(const __gri
 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN;
             epilogue_tile<BN, kBF16, kHead>(p.ep, taddr, valid, n, y, x, nt);
             tc_fence_before();
             __syncwarp();

@@ -137,7 +137,7 @@ struct Op {
     std::string name;
     // conv
     ConvParams cp;
-    int BN = 0, BK = 0;
+    int BN = 0, BK = 0, MT = 1;
     bool head = false;
     int grid = 0;
     double flops = 0;  // algorithmic (true MACs*2), not padded
@@ -170,6 +170,7 @@ struct w2l_ctx {
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
     bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
+    bool use_mt2 = true;    // W2L_DISABLE_MT2=1
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
@@ -239,11 +240,14 @@ static void free_plan(Plan* pl) {
 // conv kernel dispatch
 // ------------------------------------------------------------------------------------------------
 typedef void (*ConvKernelFn)(const ConvParams);
-struct ConvKernelEntry { int BN, BK; bool bf16, head; ConvKernelFn fn; int smem; bool attr_set; };
+struct ConvKernelEntry { int BN, BK; bool bf16, head; ConvKernelFn fn; int smem; bool attr_set; int mt; int threads; };
 
-#define W2L_CONV_ENTRY(BN_, BK_)                                                                                      \
-    {BN_, BK_, false, false, conv_igemm_kernel<BN_, BK_, false, false>, ConvCfg<BN_, BK_>::kSmemBytes, false},        \
-    {BN_, BK_, true, false, conv_igemm_kernel<BN_, BK_, true, false>, ConvCfg<BN_, BK_>::kSmemBytes, false}
+#define W2L_CONV_ENTRY(BN_, BK_)                                                                                               \
+    {BN_, BK_, false, false, conv_igemm_kernel<BN_, BK_, false, false>, ConvCfg<BN_, BK_>::kSmemBytes, false, 1, 256},         \
+    {BN_, BK_, true, false, conv_igemm_kernel<BN_, BK_, true, false>, ConvCfg<BN_, BK_>::kSmemBytes, false, 1, 256}
+#define W2L_CONV_ENTRY_MT2(BN_, BK_)                                                                                           \
+    {BN_, BK_, false, false, conv_igemm_kernel<BN_, BK_, false, false, 2>, ConvCfg<BN_, BK_, 2>::kSmemBytes, false, 2, 384},   \
+    {BN_, BK_, true, false, conv_igemm_kernel<BN_, BK_, true, false, 2>, ConvCfg<BN_, BK_, 2>::kSmemBytes, false, 2, 384}
 
 static ConvKernelEntry g_conv_kernels[] = {
     W2L_CONV_ENTRY(16, 16), W2L_CONV_ENTRY(16, 32), W2L_CONV_ENTRY(16, 64),
@@ -251,13 +255,14 @@ static ConvKernelEntry g_conv_kernels[] = {
     W2L_CONV_ENTRY(64, 16), W2L_CONV_ENTRY(64, 32), W2L_CONV_ENTRY(64, 64),
     W2L_CONV_ENTRY(128, 16), W2L_CONV_ENTRY(128, 32), W2L_CONV_ENTRY(128, 64),
     W2L_CONV_ENTRY(256, 64),
-    {32, 16, false, true, conv_igemm_kernel<32, 16, false, true>, ConvCfg<32, 16>::kSmemBytes, false},
-    {32, 16, true, true, conv_igemm_kernel<32, 16, true, true>, ConvCfg<32, 16>::kSmemBytes, false},
+    W2L_CONV_ENTRY_MT2(128, 64), W2L_CONV_ENTRY_MT2(64, 64), W2L_CONV_ENTRY_MT2(64, 32),
+    {32, 16, false, true, conv_igemm_kernel<32, 16, false, true>, ConvCfg<32, 16>::kSmemBytes, false, 1, 256},
+    {32, 16, true, true, conv_igemm_kernel<32, 16, true, true>, ConvCfg<32, 16>::kSmemBytes, false, 1, 256},
 };
 
-static ConvKernelEntry* find_conv_kernel(int BN, int BK, bool bf16, bool head) {
+static ConvKernelEntry* find_conv_kernel(int BN, int BK, bool bf16, bool head, int mt = 1) {
     for (auto& e : g_conv_kernels)
-        if (e.BN == BN && e.BK == BK && e.bf16 == bf16 && e.head == head) return &e;
+        if (e.BN == BN && e.BK == BK && e.bf16 == bf16 && e.head == head && e.mt == mt) return &e;
     return nullptr;
 }
 
@@ -311,13 +316,13 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
         ctx->launches++;
         return W2L_OK;
     }
-    ConvKernelEntry* e = find_conv_kernel(op.BN, op.BK, ctx->bf16, op.head);
-    if (!e) return fail(W2L_EINVAL, "no conv kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
+    ConvKernelEntry* e = find_conv_kernel(op.BN, op.BK, ctx->bf16, op.head, op.MT);
+    if (!e) return fail(W2L_EINVAL, "no conv kernel for BN=%d BK=%d head=%d MT=%d", op.BN, op.BK, (int)op.head, op.MT);
     if (!e->attr_set) {
         CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));
         e->attr_set = true;
     }
-    e->fn<<<op.grid, kConvThreads, e->smem, st>>>(op.cp);
+    e->fn<<<op.grid, e->threads, e->smem, st>>>(op.cp);
     ctx->launches++;
     return W2L_OK;
 }
@@ -551,6 +556,12 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
         while (BN > 32 && m_tiles * (a.cout / BN) < ctx->num_sms && a.cout % (BN / 2) == 0) BN /= 2;
     if (w.cout_pad % BN != 0) return fail(W2L_EINVAL, "%s: cout_pad %d vs BN %d", a.name.c_str(), w.cout_pad, BN);
     op.BN = BN; op.BK = BK; op.head = a.head;
+    // two M tiles per CTA (shared weight slab, two accumulators) once there is plenty of work
+    const int n_tiles_ = a.cout / BN;
+    if (ctx->use_mt2 && !a.head && find_conv_kernel(BN, BK, ctx->bf16, false, 2) &&
+        (long long)((m_tiles + 1) / 2) * n_tiles_ >= 2LL * ctx->num_sms)
+        op.MT = 2;
+    if (op.MT == 2) op.name += " [2M]";
 
     ConvParams& p = op.cp;
     memset(&p, 0, sizeof(p));
@@ -560,11 +571,11 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     p.bw = bw; p.bh = bh; p.bn = bn;
     p.sx = a.sx; p.sy = a.sy;
     p.ntaps = w.ntaps; p.kc_per_tap = w.cin_pad / BK;
-    p.stage_tx_bytes = (unsigned)(bw * bh * bn * BK * 2 + BN * BK * 2);
+    p.stage_tx_bytes = (unsigned)(op.MT * bw * bh * bn * BK * 2 + BN * BK * 2);
     fill_epi(&p.ep, a);
     if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
     for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; }
-    const int total = m_tiles * p.n_tiles;
+    const int total = ((m_tiles + op.MT - 1) / op.MT) * p.n_tiles;
     op.grid = std::min(total, ctx->num_sms);
     op.flops = 2.0 * a.macs_per_pixel * (double)a.Wl * a.Hl * a.in.N;
     pl->ops.push_back(op);
@@ -1236,6 +1247,8 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_fold = !(e2 && e2[0] == '1');
         const char* e3 = getenv("W2L_DISABLE_BN256");
         ctx->use_bn256 = !(e3 && e3[0] == '1');
+        const char* e5 = getenv("W2L_DISABLE_MT2");
+        ctx->use_mt2 = !(e5 && e5[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
         ctx->use_ctfused = !(e4 && e4[0] == '1');
         if (ctx->use_fold) {
