@@ -95,12 +95,32 @@ class ClockSampler:
                 "reasons": sorted(reasons)}
 
 
-def cpu_baseline_run(n, threads, repeats=1):
+def pick_threads(sd, O, torch):
+    """torch's CPU conv does not scale to every hardware thread of a large host (128 threads were 8x SLOWER than
+    32 on the B200 box): calibrate on a small batch and give the reference arm its best thread count."""
+    cores = os.cpu_count() or 1
+    cands = sorted({c for c in (8, 16, 32, 64, cores) if c <= cores})
+    mel, face = O.make_generator_inputs(8, 1)
+    best, best_t = None, cands[-1]
+    for c in cands:
+        torch.set_num_threads(c)
+        with torch.no_grad():
+            O.generator_forward(sd, mel[:2], face[:2])
+            t0 = time.perf_counter()
+            O.generator_forward(sd, mel, face)
+            dt = time.perf_counter() - t0
+        if best is None or dt < best:
+            best, best_t = dt, c
+    torch.set_num_threads(best_t)
+    return best_t
+
+
+def cpu_baseline_run(n, repeats=1):
     """The oracle port (the reference's own CPU arithmetic: torch fp32 conv/BN/ReLU) on the host cores."""
     import torch
     from oracle import w2l_oracle as O
-    torch.set_num_threads(threads)
     sd = O.make_state_dict("generator", 0, init="default")
+    threads = pick_threads(sd, O, torch)
     mel, face = O.make_generator_inputs(n, 0)
     with torch.no_grad():
         O.generator_forward(sd, mel[:2], face[:2])  # warm the thread pool / primitive cache
@@ -110,7 +130,51 @@ def cpu_baseline_run(n, threads, repeats=1):
             O.generator_forward(sd, mel, face)
             dt = time.perf_counter() - t0
             best = dt if best is None else min(best, dt)
-    return n / best, best
+    return n / best, best, threads
+
+
+def measure_extra(dev):
+    """SyncNet_color B=256, Wav2Lip_disc_qual B=256 x T=5, audio.melspectrogram 10 k and 1 M frames: CUDA-event
+    times of the other entry points of the path (BASELINE configs[2] and [3]); random default-init weights."""
+    import numpy as np
+    import torch
+    from wav2lip_b200 import audio
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip_disc_qual
+    out = {}
+
+    def timeit(fn, iters):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        return e0.elapsed_time(e1) / iters
+
+    with torch.no_grad():
+        torch.manual_seed(2)
+        s = SyncNet_color().to(dev).eval()
+        mel = (torch.rand((256, 1, 80, 16)) * 8 - 4).to(dev)
+        face = torch.rand((256, 15, 48, 96)).to(dev)
+        ms = timeit(lambda: s(mel, face), 10)
+        out["syncnet"] = {"config": "SyncNet_color.forward B=256 (fp16 operands)", "ms": ms, "windows_per_s": 256 / ms * 1e3,
+                          "tflops": 256 / ms * 1e3 * 2 * 1210281984 / 1e12}
+        del s
+        d = Wav2Lip_disc_qual().to(dev).eval()
+        frames = torch.rand((256, 3, 5, 96, 96)).to(dev)
+        ms = timeit(lambda: d(frames), 10)
+        out["disc"] = {"config": "Wav2Lip_disc_qual.forward B=256, T=5 (1280 frames, fp16 operands)", "ms": ms,
+                       "frames_per_s": 1280 / ms * 1e3, "tflops": 1280 / ms * 1e3 * 2 * 1255850496 / 1e12}
+        del d, frames
+        for nfr, key in ((10000, "mel_10k"), (1000000, "mel_1M")):
+            wav = (0.1 * torch.randn((nfr - 1) * 200, device=dev)).float()
+            ms = timeit(lambda: audio.melspectrogram(wav), 10)
+            out[key] = {"config": f"audio.melspectrogram, {nfr} frames ({wav.numel()} samples) resident on the device",
+                        "ms": ms, "frames_per_s": nfr / ms * 1e3, "algorithmic_GBps": nfr * 1120 / ms / 1e6}
+    return out
 
 
 def run_reference(args, rank, world):
@@ -119,11 +183,10 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    cores = os.cpu_count() or 1
     n = 128  # one inference.py batch (inference.py:33) per step: a bounded sample of the 640-crop workload
     from oracle import w2l_oracle as O
-    torch.set_num_threads(cores)
     sd = O.make_state_dict("generator", 0, init="default")
+    cores = pick_threads(sd, O, torch)
     mel, face = O.make_generator_inputs(n, 0)
     with torch.no_grad():
         for _ in range(max(1, min(args.warmup, 2))):
@@ -141,7 +204,7 @@ def run_reference(args, rank, world):
         "config": {"workload": "Wav2Lip.forward eval, B=128 T=5 workload sampled as one N=128 4-D batch per step",
                    "weights": "seeded random, reference default-init statistics + randomised BatchNorm"},
         "cpu_baseline": {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
-                         "sample": "N=128 crops per step (4-D call), torch CPU fp32, all host threads"},
+                         "sample": f"N=128 crops per step (4-D call), torch CPU fp32, best of 8/16/32/64/{os.cpu_count()} threads = {cores}"},
         "e2e": {"value": v, "unit": "crops/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -158,6 +221,7 @@ def main():
     ap.add_argument("--frames", type=int, default=T_DEFAULT, help="T (frames per window)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the SyncNet / disc / mel side measurements")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table to this file")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -284,13 +348,18 @@ def main():
                 for nm, m, fl in prof:
                     f.write(f"{nm:36s} {m * 1e3:10.1f} us {fl / m / 1e9 if m > 0 else 0:9.1f} TFLOP/s {100 * m / conv_ms:5.1f}%\n")
 
+    # ---- the other hot-path entry points (BASELINE configs[2], configs[3]); informational, outside the timed region ----
+    extra = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        extra = measure_extra(dev)
+
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        v, dt = cpu_baseline_run(128, cores)
+        v, dt, cores = cpu_baseline_run(128)
         cpu = {"value": v, "unit": "crops/s", "cores": cores, "kind": "port",
-               "sample": f"one N=128 4-D batch (inference.py batch) = {dt:.2f} s of oracle/w2l_oracle.py (torch CPU fp32, {cores} threads)"}
+               "sample": f"one N=128 4-D batch (inference.py batch) = {dt:.2f} s of oracle/w2l_oracle.py (torch CPU fp32; "
+                         f"{cores} threads = the fastest of 8/16/32/64/{os.cpu_count()} on this host)"}
 
     if rank == 0:
         line = {
@@ -303,6 +372,7 @@ def main():
                        "l2": "inputs larger than L2 (141 MB face + activations >> 126 MB), no explicit flush",
                        "precision": "fp16 operands / fp32 accumulate+epilogue (TF32-class mantissa)"},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
