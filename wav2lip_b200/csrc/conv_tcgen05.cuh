@@ -38,8 +38,9 @@ namespace w2l {
 constexpr int kTileM = 128;
 constexpr int kMaxTaps = 49;
 constexpr int kConvThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;  // pipeline stages; barriers etc. live in the extra KB below
+constexpr int kSmemBudget = 200 * 1024;  // patch kernels: weights + patch ring + staging; barriers live in the extra KB
 constexpr int kSmemExtra = 2048;         // 1024 alignment slack + barriers
+constexpr int kSmemMax = 227 * 1024;     // dynamic shared memory limit per CTA on sm_100
 
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_LRELU = 2 };
 
@@ -64,6 +65,10 @@ struct EpiParams {
 struct alignas(64) ConvParams {
     CUtensorMap tmA;  // activations, dims (C, W, H, N), box (BK, bw*sx, bh*sy, bn), elem strides (1,sx,sy,1)
     CUtensorMap tmB;  // weights, dims (Cin_pad, Cout_pad, taps), box (BK, BN, 1)
+    CUtensorMap tmO;  // output slice (Cout, Wl, Hl, N) with the launch's pixel strides, box (EW, bw, bh, bn)   [tma_epi]
+    CUtensorMap tmR;  // residual, same geometry                                                              [tma_epi]
+    int tma_epi;             // 1: epilogue stages through swizzled smem and uses TMA for the residual and the output
+    unsigned epi_box_bytes;  // bytes of one epilogue box (bw*bh*bn rows x EW channels)
     // M tiling of the logical output grid
     int tiles_x, tiles_y, tiles_n, n_tiles;
     int bw, bh, bn;
@@ -187,9 +192,12 @@ struct ConvCfg {
     static constexpr int kABytes = MT * kATile;
     static constexpr int kBBytes = BN * BK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagesRaw = kSmemBudget / kStageBytes;
+    static constexpr int kEW = BN < 64 ? BN : 64;                 // channels per epilogue pass
+    static constexpr int kStgTile = kTileM * kEW * 2;             // staging tile of one epilogue group
+    static constexpr int kStgBytes = MT * ((kStgTile + 1023) / 1024 * 1024);
+    static constexpr int kStagesRaw = (kSmemMax - kSmemExtra - kStgBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
-    static constexpr int kSmemBytes = kStages * kStageBytes + kSmemExtra;
+    static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + kSmemExtra;
     static constexpr int kAccCols = 2 * MT * BN;
     static constexpr int kTmemCols = (kAccCols <= 32) ? 32 : (kAccCols <= 64) ? 64 : (kAccCols <= 128) ? 128 : (kAccCols <= 256) ? 256 : 512;
     static constexpr int kThreads = 128 + 128 * MT;  // 4 control warps + 4 epilogue warps per M tile
@@ -302,12 +310,14 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // swizzle atoms need 1024-B alignment
-    const uint32_t bar_base = smem_base + kStages * Cfg::kStageBytes;
+    const uint32_t stg_base = smem_base + kStages * Cfg::kStageBytes;
+    const uint32_t bar_base = stg_base + Cfg::kStgBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 4);
+    auto res_bar = [&](int g) { return bar_base + 8u * (2 * kStages + 4 + g); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kStages + 6);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -315,6 +325,10 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
+        if (p.tma_epi) {
+            tma_prefetch_desc(&p.tmO);
+            tma_prefetch_desc(&p.tmR);
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kStages; ++s) {
@@ -325,6 +339,7 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
             mbar_init(tfull_bar(a), 1);
             mbar_init(tempty_bar(a), 4 * MT);  // one arrive per epilogue warp
         }
+        for (int g = 0; g < MT; ++g) mbar_init(res_bar(g), 1);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -417,27 +432,143 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
         const int px = row % p.bw;
         const int py = (row / p.bw) % p.bh;
         const int pn = row / (p.bw * p.bh);
-        int it = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1u;
-            const int nt = tile % p.n_tiles;
-            const int m = (tile / p.n_tiles) * MT + mt;
-            const int tx = m % p.tiles_x;
-            const int ty = (m / p.tiles_x) % p.tiles_y;
-            const int tn = m / (p.tiles_x * p.tiles_y);
-            const int x = tx * p.bw + px;
-            const int y = ty * p.bh + py;
-            const int n = tn * p.bn + pn;
-            const bool valid = (row < rows_valid) && (x < p.ep.Wout) && (y < p.ep.Hout) && (n < p.ep.N);
+        if (!kHead && p.tma_epi) {
+            // ---- staged epilogue: residual in by TMA, result out by TMA, one swizzled smem tile per group ----
+            constexpr int EW = Cfg::kEW;
+            constexpr int kPasses = BN / EW;
+            constexpr uint32_t kRowB = EW * 2;
+            constexpr uint32_t kSwz = (kRowB == 128) ? 7u : (kRowB == 64) ? 3u : 1u;
+            const uint32_t stg = stg_base + mt * ((Cfg::kStgTile + 1023) / 1024 * 1024);
+            const bool leader = (q == 0 && lane == 0);
+            const uint32_t bar_id = 1 + mt;
+            const bool has_res = p.ep.res != nullptr;
+            const EpiParams& e = p.ep;
+            auto tile_origin = [&](int tile_, int* nt_, int* x0_, int* y0_, int* n0_) {
+                *nt_ = tile_ % p.n_tiles;
+                const int m_ = (tile_ / p.n_tiles) * MT + mt;
+                *x0_ = (m_ % p.tiles_x) * p.bw;
+                *y0_ = ((m_ / p.tiles_x) % p.tiles_y) * p.bh;
+                *n0_ = (m_ / (p.tiles_x * p.tiles_y)) * p.bn;
+            };
+            uint32_t rphase = 0;
+            if (has_res && leader && static_cast<int>(blockIdx.x) < total_tiles) {
+                int nt0, x0, y0, n0;
+                tile_origin(blockIdx.x, &nt0, &x0, &y0, &n0);
+                mbar_arrive_expect_tx(res_bar(mt), p.epi_box_bytes);
+                tma_load_4d(stg, &p.tmR, res_bar(mt), nt0 * BN, x0, y0, n0);
+            }
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                int nt, x0, y0, n0;
+                tile_origin(tile, &nt, &x0, &y0, &n0);
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN;
+#pragma unroll 1
+                for (int ps = 0; ps < kPasses; ++ps) {
+                    uint32_t v[EW];
+#pragma unroll
+                    for (int c0 = 0; c0 < EW; c0 += 16) tmem_ld16(taddr + ps * EW + c0, v + c0);
+                    tmem_ld_wait();
+                    if (ps == kPasses - 1) {  // accumulator fully read: release the TMEM stage
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tempty_bar(acc));
+                    }
+                    if (has_res) {
+                        mbar_wait(res_bar(mt), rphase);
+                        rphase ^= 1u;
+                    }
+                    const int cg = nt * BN + ps * EW;
+#pragma unroll
+                    for (int j = 0; j < EW / 8; ++j) {
+                        float f[8];
+                        const float4 s0 = __ldg(reinterpret_cast<const float4*>(e.scale + cg + 8 * j));
+                        const float4 s1 = __ldg(reinterpret_cast<const float4*>(e.scale + cg + 8 * j + 4));
+                        const float4 h0 = __ldg(reinterpret_cast<const float4*>(e.shift + cg + 8 * j));
+                        const float4 h1 = __ldg(reinterpret_cast<const float4*>(e.shift + cg + 8 * j + 4));
+                        f[0] = fmaf(__uint_as_float(v[8 * j + 0]), s0.x, h0.x);
+                        f[1] = fmaf(__uint_as_float(v[8 * j + 1]), s0.y, h0.y);
+                        f[2] = fmaf(__uint_as_float(v[8 * j + 2]), s0.z, h0.z);
+                        f[3] = fmaf(__uint_as_float(v[8 * j + 3]), s0.w, h0.w);
+                        f[4] = fmaf(__uint_as_float(v[8 * j + 4]), s1.x, h1.x);
+                        f[5] = fmaf(__uint_as_float(v[8 * j + 5]), s1.y, h1.y);
+                        f[6] = fmaf(__uint_as_float(v[8 * j + 6]), s1.z, h1.z);
+                        f[7] = fmaf(__uint_as_float(v[8 * j + 7]), s1.w, h1.w);
+                        uint32_t a = stg + row * kRowB + j * 16;
+                        a ^= ((a >> 7) & kSwz) << 4;
+                        if (has_res) {
+                            uint32_t r0, r1, r2, r3;
+                            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(a));
+                            const float2 a0 = unpack2<kBF16>(r0), a1 = unpack2<kBF16>(r1);
+                            const float2 a2 = unpack2<kBF16>(r2), a3 = unpack2<kBF16>(r3);
+                            f[0] += a0.x; f[1] += a0.y; f[2] += a1.x; f[3] += a1.y;
+                            f[4] += a2.x; f[5] += a2.y; f[6] += a3.x; f[7] += a3.y;
+                        }
+                        if (e.act == ACT_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = fmaxf(f[i], 0.0f);
+                        } else if (e.act == ACT_LRELU) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.01f * f[i];
+                        }
+                        const uint32_t o0 = pack2<kBF16>(f[0], f[1]), o1 = pack2<kBF16>(f[2], f[3]);
+                        const uint32_t o2 = pack2<kBF16>(f[4], f[5]), o3 = pack2<kBF16>(f[6], f[7]);
+                        asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+                    }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                    if (leader) {
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&p.tmO)), "r"(stg), "r"(cg), "r"(x0), "r"(y0), "r"(n0)
+                                     : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the store has read the tile
+                        if (has_res) {  // fetch the residual of the next pass / next tile into the (now free) tile
+                            int nnt = nt, nx0 = x0, ny0 = y0, nn0 = n0, nps = ps + 1;
+                            bool more = true;
+                            if (nps == kPasses) {
+                                nps = 0;
+                                const int ntile = tile + static_cast<int>(gridDim.x);
+                                more = ntile < total_tiles;
+                                if (more) tile_origin(ntile, &nnt, &nx0, &ny0, &nn0);
+                            }
+                            if (more) {
+                                mbar_arrive_expect_tx(res_bar(mt), p.epi_box_bytes);
+                                tma_load_4d(stg, &p.tmR, res_bar(mt), nnt * BN + nps * EW, nx0, ny0, nn0);
+                            }
+                        }
+                    }
+                    // everyone else must not touch the tile again before the leader is past wait_group.read
+                    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+                }
+            }
+            if (leader) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        } else {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                const int nt = tile % p.n_tiles;
+                const int m = (tile / p.n_tiles) * MT + mt;
+                const int tx = m % p.tiles_x;
+                const int ty = (m / p.tiles_x) % p.tiles_y;
+                const int tn = m / (p.tiles_x * p.tiles_y);
+                const int x = tx * p.bw + px;
+                const int y = ty * p.bh + py;
+                const int n = tn * p.bn + pn;
+                const bool valid = (row < rows_valid) && (x < p.ep.Wout) && (y < p.ep.Hout) && (n < p.ep.N);
 
-            mbar_wait(tfull_bar(acc), acc_phase);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN;
-            epilogue_tile<BN, kBF16, kHead>(p.ep, taddr, valid, n, y, x, nt);
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));
+                mbar_wait(tfull_bar(acc), acc_phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * (MT * BN) + mt * BN;
+                epilogue_tile<BN, kBF16, kHead>(p.ep, taddr, valid, n, y, x, nt);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tempty_bar(acc));
+            }
         }
     }
 

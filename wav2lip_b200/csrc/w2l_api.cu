@@ -171,6 +171,7 @@ struct w2l_ctx {
     bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
     bool use_mt2 = true;    // W2L_DISABLE_MT2=1
+    bool use_tma_epi = true;  // W2L_DISABLE_TMAEPI=1
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
@@ -573,6 +574,31 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     p.ntaps = w.ntaps; p.kc_per_tap = w.cin_pad / BK;
     p.stage_tx_bytes = (unsigned)(op.MT * bw * bh * bn * BK * 2 + BN * BK * 2);
     fill_epi(&p.ep, a);
+    // staged epilogue (TMA residual load + TMA store) for 16-bit outputs; the head / fp32 outputs keep direct stores
+    p.tma_epi = 0;
+    if (ctx->use_tma_epi && !a.head && !a.out.f32) {
+        EncodeTiledFn enc = get_encode_fn();
+        const int EW = BN < 64 ? BN : 64;
+        const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const CUtensorMapSwizzle esw = EW == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : EW == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+        cuuint64_t dims[4] = {(cuuint64_t)a.cout, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
+        cuuint32_t box[4] = {(cuuint32_t)EW, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        cuuint64_t os[3] = {(cuuint64_t)p.ep.out_sx * 2, (cuuint64_t)p.ep.out_sy * 2, (cuuint64_t)p.ep.out_sn * 2};
+        CUresult r = enc(&p.tmO, dt, 4, p.ep.out, dims, os, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, esw,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(out) failed with %d", a.name.c_str(), (int)r);
+        if (a.res) {
+            cuuint64_t rs[3] = {(cuuint64_t)p.ep.res_sx * 2, (cuuint64_t)p.ep.res_sy * 2, (cuuint64_t)p.ep.res_sn * 2};
+            r = enc(&p.tmR, dt, 4, const_cast<void*>(p.ep.res), dims, rs, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, esw,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(res) failed with %d", a.name.c_str(), (int)r);
+        } else {
+            p.tmR = p.tmO;
+        }
+        p.tma_epi = 1;
+        p.epi_box_bytes = (unsigned)(bw * bh * bn * EW * 2);
+    }
     if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
     for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; }
     const int total = ((m_tiles + op.MT - 1) / op.MT) * p.n_tiles;
@@ -1247,6 +1273,8 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_fold = !(e2 && e2[0] == '1');
         const char* e3 = getenv("W2L_DISABLE_BN256");
         ctx->use_bn256 = !(e3 && e3[0] == '1');
+        const char* e6 = getenv("W2L_DISABLE_TMAEPI");
+        ctx->use_tma_epi = !(e6 && e6[0] == '1');
         const char* e5 = getenv("W2L_DISABLE_MT2");
         ctx->use_mt2 = !(e5 && e5[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
