@@ -169,6 +169,31 @@ def measure_extra(dev):
         out["disc"] = {"config": "Wav2Lip_disc_qual.forward B=256, T=5 (1280 frames, fp16 operands)", "ms": ms,
                        "frames_per_s": 1280 / ms * 1e3, "tflops": 1280 / ms * 1e3 * 2 * 1255850496 / 1e12}
         del d, frames
+        # fused uint8 batch assembly (scope row f): host uint8 crops + fp32 mels in, host uint8 predictions out
+        import ctypes as C
+        from wav2lip_b200 import _lib
+        from wav2lip_b200.models import Wav2Lip
+        g = Wav2Lip().to(dev).eval()
+        g._ensure(torch.zeros(1, device=dev))
+        ctx = g._w2l_ctx
+        n = 640
+        faces = torch.randint(0, 256, (n, 96, 96, 3), dtype=torch.uint8).pin_memory()
+        melh = (torch.rand((n, 1, 80, 16)) * 8 - 4).pin_memory()
+        outh = torch.empty((n, 96, 96, 3), dtype=torch.uint8).pin_memory()
+
+        def u8_step():
+            _lib.check(ctx.lib.w2l_generator_forward_u8_host(ctx.h, C.c_void_p(melh.data_ptr()), C.c_void_p(faces.data_ptr()),
+                                                             C.c_void_p(outh.data_ptr()), n))
+        for _ in range(3):
+            u8_step()
+        t0 = time.perf_counter()
+        for _ in range(10):
+            u8_step()
+        dt = (time.perf_counter() - t0) / 10
+        out["e2e_u8"] = {"config": "w2l_generator_forward_u8_host: 640 uint8 96x96x3 crops + fp32 mels from pinned host memory, "
+                                   "uint8 predictions back (inference.py:134-140,259-265,269 fused)", "ms": dt * 1e3,
+                         "crops_per_s": n / dt, "h2d_bytes": int(faces.numel() + melh.numel() * 4), "d2h_bytes": int(outh.numel())}
+        del g
         for nfr, key in ((10000, "mel_10k"), (1000000, "mel_1M")):
             wav = (0.1 * torch.randn((nfr - 1) * 200, device=dev)).float()
             ms = timeit(lambda: audio.melspectrogram(wav), 10)

@@ -96,6 +96,17 @@ int w2l_generator_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_
 int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_host, const float* face_host,
                                float* out_host, int B, int T);
 
+/* Scope row (f): the batch assembly around the generator call of inference.py, fused on the GPU.
+ * Replaces inference.py:134-140 (mask the lower half, concat [masked | full] on channels, /255, NHWC->NCHW),
+ * :259-263 (to device, forward) and :265,:269 (transpose, *255., astype(uint8)) — everything between the
+ * cv2.resize of the crop (:126) and the cv2.resize of the prediction (:269):
+ *   mel (N,1,80,16) fp32, faces (N,96,96,3) uint8 BGR crops -> out (N,96,96,3) uint8 BGR.
+ * 8x fewer H2D and 4x fewer D2H bytes than the fp32 call. */
+int w2l_generator_forward_u8(w2l_ctx* ctx, const float* mel_dev, const uint8_t* faces_dev, uint8_t* out_dev,
+                             int N, void* stream);
+int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_host, const uint8_t* faces_host,
+                                  uint8_t* out_host, int N);
+
 /* Replaces `SyncNet_color.forward(audio, face)` (syncnet.py:55-66):
  *   mel (B,1,80,16), face (B,15,48,96) -> audio_emb (B,512), face_emb (B,512), both L2-normalised. */
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_dev,
@@ -128,6 +139,19 @@ int w2l_melspectrogram(w2l_ctx* ctx, const float* wav_dev, int64_t n_samples, fl
 int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_host, int64_t n_samples, float* mel_host);
 /* number of frames for n_samples: 1 + n_samples/200 (librosa center=True) */
 int64_t w2l_mel_num_frames(int64_t n_samples);
+
+/* Scope row (f): replaces the mel chunking loop of inference.py:231-240 — chunk i = mel[:, s_i : s_i+16] with
+ * s_i = int(i * 80./fps), the last chunk right-aligned; chunks out is (n_chunks,1,80,16) fp32, i.e. already the
+ * `mel_batch` layout of inference.py:260.  w2l_mel_num_chunks gives n_chunks for a mel of n_frames columns. */
+int64_t w2l_mel_num_chunks(int64_t n_frames, double fps);
+int w2l_mel_chunks(w2l_ctx* ctx, const float* mel_dev, int64_t n_frames, double fps, float* chunks_dev,
+                   int64_t n_chunks, void* stream);
+
+/* ---- test aids ---- */
+/* keep every block output of subsequent plans addressable (no buffer reuse) for w2l_debug_layer_output */
+int w2l_set_debug(w2l_ctx* ctx, int keep_all_layer_outputs);
+/* the kernel's own (80 x 401) Slaney mel filterbank, dense fp32, written to HOST memory */
+int w2l_mel_basis_host(float* out_host);
 
 /* ---- instrumentation ---- */
 /* kernels launched by this library since the context was created (all streams) */

@@ -1,0 +1,81 @@
+"""Scope rows (f): the mel chunker (inference.py:231-240) and the fused uint8 batch assembly around the
+generator call (inference.py:134-140, 259-265, 269).  CPU part: chunk counting (host logic in libw2l) against
+the verbatim NumPy restatement.  GPU part: kernels against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mel_oracle as M
+from oracle import pipeline_oracle as P
+from oracle import w2l_oracle as O
+
+
+def test_mel_num_chunks_host_logic():
+    from wav2lip_b200 import _lib
+    L = _lib.get_lib()
+    for fps in (25.0, 24.0, 30.0, 23.976, 29.97, 50.0, 12.5, 60.0):
+        for F in (16, 17, 31, 32, 80, 81, 241, 1000, 10000, 12345):
+            mel = np.zeros((80, F), dtype=np.float32)
+            assert L.w2l_mel_num_chunks(F, fps) == len(P.mel_chunks(mel, fps)), (F, fps)
+    assert L.w2l_mel_num_chunks(15, 25.0) == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fps", [25.0, 29.97, 24.0])
+def test_mel_chunks_bit_exact(fps):
+    from wav2lip_b200 import audio
+    wav = M.make_wav(16000 * 3 + 77, seed=4, kind="mix")
+    mel = M.melspectrogram(wav)
+    ref = np.stack(P.mel_chunks(mel, fps))[:, None]            # (n,1,80,16)
+    got = audio.mel_chunks(mel, fps)
+    assert got.shape == ref.shape
+    assert np.array_equal(got, ref)                             # pure gather: bit-exact
+    # device path: mel computed and chunked on the GPU without touching the host
+    mel_dev = audio.melspectrogram(torch.from_numpy(wav).cuda())
+    chunks_dev = audio.mel_chunks(mel_dev, fps)
+    assert chunks_dev.is_cuda and tuple(chunks_dev.shape) == ref.shape
+    assert np.abs(chunks_dev.cpu().numpy() - ref).max() <= 1e-4
+    with pytest.raises(ValueError):
+        audio.mel_chunks(np.zeros((80, 10), dtype=np.float32), fps)
+
+
+@pytest.mark.gpu
+def test_fused_u8_assembly_matches_reference_pipeline():
+    """faces uint8 -> [mask | full]/255 -> generator -> *255 -> uint8, against the oracle running the reference's
+    own NumPy lines + the fp32 CPU generator.  Integer output through a float pipeline: |diff| <= 1 LSB, and
+    the large majority of bytes identical."""
+    import ctypes as C
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import Wav2Lip
+    rng = np.random.RandomState(3)
+    N = 5
+    faces = rng.randint(0, 256, size=(N, 96, 96, 3), dtype=np.uint8)
+    wav = M.make_wav(16000, seed=9, kind="noise")
+    mels = P.mel_chunks(M.melspectrogram(wav), 25.0)[:N]
+    mel_b, img_b = P.assemble_batch(faces, mels)
+    sd = O.make_state_dict("generator", 0, init="default")
+    with torch.no_grad():
+        pred = O.generator_forward(sd, torch.from_numpy(mel_b), torch.from_numpy(img_b)).numpy()
+    ref = P.postprocess(pred)
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    with torch.no_grad():
+        out = g.infer_u8(torch.from_numpy(mel_b).cuda(), torch.from_numpy(faces).cuda())
+        # the fp32 call on the oracle-assembled batch must agree with the fused path as well
+        y32 = g(torch.from_numpy(mel_b).cuda(), torch.from_numpy(img_b).cuda()).cpu().numpy()
+    out = out.cpu().numpy()
+    assert out.shape == ref.shape and out.dtype == np.uint8
+    d = np.abs(out.astype(np.int16) - ref.astype(np.int16))
+    assert d.max() <= 1
+    assert (d == 0).mean() >= 0.98
+    assert np.array_equal(out, P.postprocess(y32))              # fused assembly == explicit assembly, bit for bit
+    # host-buffer variant (pipelined) gives the same bytes
+    ctx = g._w2l_ctx
+    out_h = np.empty_like(out)
+    mel_h = np.ascontiguousarray(mel_b)
+    _lib.check(ctx.lib.w2l_generator_forward_u8_host(ctx.h, mel_h.ctypes.data_as(C.c_void_p), faces.ctypes.data_as(C.c_void_p),
+                                                     out_h.ctypes.data_as(C.c_void_p), N))
+    assert np.array_equal(out_h, out)
+    with pytest.raises(ValueError):
+        g.infer_u8(torch.from_numpy(mel_b).cuda(), torch.zeros((N, 96, 96, 3), device="cuda"))

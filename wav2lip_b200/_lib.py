@@ -21,10 +21,11 @@ PREC_F16, PREC_BF16 = 0, 1
 EXPORTS = [
     "w2l_abi_version", "w2l_last_error", "w2l_net_num_layers", "w2l_net_layer_info",
     "w2l_create", "w2l_destroy", "w2l_load_weights",
-    "w2l_generator_forward", "w2l_generator_forward_host", "w2l_syncnet_forward", "w2l_disc_forward",
+    "w2l_generator_forward", "w2l_generator_forward_host", "w2l_generator_forward_u8", "w2l_generator_forward_u8_host",
+    "w2l_syncnet_forward", "w2l_disc_forward",
     "w2l_conv_block_forward", "w2l_debug_layer_output",
-    "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames",
-    "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
+    "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
+    "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
 ]
 
 
@@ -66,6 +67,11 @@ def get_lib() -> C.CDLL:
     lib.w2l_load_weights.argtypes = [vp, i32, i32, C.POINTER(cp), C.POINTER(vp), C.POINTER(i64), vp]
     lib.w2l_generator_forward.argtypes = [vp, vp, vp, vp, i32, i32, vp]
     lib.w2l_generator_forward_host.argtypes = [vp, vp, vp, vp, i32, i32]
+    lib.w2l_generator_forward_u8.argtypes = [vp, vp, vp, vp, i32, vp]
+    lib.w2l_generator_forward_u8_host.argtypes = [vp, vp, vp, vp, i32]
+    lib.w2l_mel_num_chunks.argtypes = [i64, C.c_double]
+    lib.w2l_mel_num_chunks.restype = i64
+    lib.w2l_mel_chunks.argtypes = [vp, vp, i64, C.c_double, vp, i64, vp]
     lib.w2l_syncnet_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.w2l_disc_forward.argtypes = [vp, vp, vp, i32, i32, vp]
     lib.w2l_conv_block_forward.argtypes = [vp, C.POINTER(LayerInfo), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]

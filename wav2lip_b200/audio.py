@@ -66,6 +66,35 @@ def melspectrogram(wav, device: int = 0):
     return out
 
 
+def num_chunks(n_frames: int, fps: float) -> int:
+    return int(_lib().get_lib().w2l_mel_num_chunks(int(n_frames), float(fps)))
+
+
+def mel_chunks(mel, fps: float, device: int = 0):
+    """inference.py:231-240 on the GPU: (80,F) mel -> (n_chunks,1,80,16) chunks, one per video frame at `fps`
+    (start = int(i*80./fps), last chunk right-aligned) — already the `mel_batch` layout of inference.py:260.
+    CUDA tensor in -> CUDA tensor out; numpy in -> numpy out."""
+    import torch
+    L = _lib()
+    is_np = not isinstance(mel, torch.Tensor)
+    m = torch.as_tensor(np.ascontiguousarray(mel) if is_np else mel).float()
+    if m.dim() != 2 or m.shape[0] != 80:
+        raise ValueError(f"expected an (80, F) mel, got {tuple(m.shape)}")
+    if not m.is_cuda:
+        m = m.cuda(device)
+    m = m.contiguous()
+    F = m.shape[1]
+    n = num_chunks(F, fps)
+    if n <= 0:
+        raise ValueError(f"mel has {F} frames: shorter than one 16-frame chunk")
+    ctx = _context(m.device.index or 0)
+    out = torch.empty((n, 1, 80, 16), device=m.device, dtype=torch.float32)
+    stream = torch.cuda.current_stream(m.device).cuda_stream
+    L.check(ctx.lib.w2l_mel_chunks(ctx.h, C.c_void_p(m.data_ptr()), F, float(fps), C.c_void_p(out.data_ptr()), n,
+                                   C.c_void_p(stream)))
+    return out.cpu().numpy() if is_np else out
+
+
 def mel_basis() -> np.ndarray:
     """The kernel's own (80, 401) Slaney filterbank (host computation in libw2l), for inspection."""
     L = _lib()

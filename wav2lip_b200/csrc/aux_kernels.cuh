@@ -71,6 +71,58 @@ __global__ void ingest_kernel(const IngestParams p) {
     }
 }
 
+// Batch assembly of inference.py:134-140 on the GPU: uint8 BGR crops (N,96,96,3) -> 6 channels
+// [crop with rows >= H/2 zeroed | crop] / 255 (float64 division rounded to float32, as np.concatenate(...)/255.
+// followed by torch.FloatTensor does), written in the first conv's input layout.
+struct IngestU8Params {
+    const unsigned char* src;  // (N, H, W, 3)
+    uint16_t* dst;
+    int N, H, W, Cpad, Wp, x_off;
+};
+
+template <bool kBF16>
+__global__ void ingest_u8_kernel(const IngestU8Params p) {
+    const long long total = (long long)p.N * p.H * p.W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % p.W);
+        const int y = (int)((i / p.W) % p.H);
+        const int n = (int)(i / ((long long)p.W * p.H));
+        const unsigned char* s = p.src + i * 3;
+        uint16_t h[8];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float v = (float)((double)s[c] / 255.0);
+            h[3 + c] = to16<kBF16>(v);
+            h[c] = (y >= p.H / 2) ? (uint16_t)0 : h[3 + c];
+        }
+        h[6] = h[7] = 0;
+        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpad;
+        uint4 o;
+        o.x = h[0] | ((uint32_t)h[1] << 16);
+        o.y = h[2] | ((uint32_t)h[3] << 16);
+        o.z = h[4] | ((uint32_t)h[5] << 16);
+        o.w = 0u;
+        *reinterpret_cast<uint4*>(d) = o;
+        for (int c0 = 8; c0 < p.Cpad; c0 += 8) *reinterpret_cast<uint4*>(d + c0) = make_uint4(0u, 0u, 0u, 0u);
+    }
+}
+
+// Mel chunking of inference.py:231-240: chunk i = mel[:, start_i : start_i + 16], start_i = int(i * 80./fps);
+// the last chunk is right-aligned (mel[:, F-16:]).  out is (n_chunks, 1, 80, 16) fp32.
+__global__ void mel_chunk_kernel(const float* mel, long long F, double mult, int n_chunks, float* out) {
+    const long long total = (long long)n_chunks * 80 * 16;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i % 16);
+        const int m = (int)((i / 16) % 80);
+        const int c = (int)(i / 1280);
+        long long start = (long long)((double)c * mult);
+        if (start + 16 > F) start = F - 16;
+        out[i] = mel[(long long)m * F + start + t];
+    }
+}
+
 // NHWC 16-bit (channel slice of a buffer with channel pitch Cs) -> NCHW fp32
 template <bool kBF16>
 __global__ void export_kernel(const uint16_t* src, float* dst, int N, int H, int W, int C, int Cs, int f32src) {

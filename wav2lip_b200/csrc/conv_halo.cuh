@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
 #pragma unroll
                         for (int j = 0; j < 32; ++j) s = fmaf(f[j], p.chead_w[oc * 32 + j], s);
                         s = 1.0f / (1.0f + __expf(-s));
-                        e.head_out[(((long long)hb * 3 + oc) * e.head_T + ht) * plane + (long long)y * e.Wout + x] = s;
+                        if (e.head_out_u8 != nullptr)
+                            e.head_out_u8[(((long long)n * e.Hout + y) * e.Wout + x) * 3 + oc] = (unsigned char)__fmul_rn(s, 255.0f);
+                        else
+                            e.head_out[(((long long)hb * 3 + oc) * e.head_T + ht) * plane + (long long)y * e.Wout + x] = s;
                     }
                 }
             } else {

@@ -59,6 +59,7 @@ struct EpiParams {
     const float* head_w;
     const float* head_b;
     float* head_out;
+    unsigned char* head_out_u8;  // if set: (N,H,W,3) uint8 = trunc(sigmoid * 255.f), inference.py:265,269
     int head_B, head_T;     // n = t*head_B + b ; T=1,B=N for the 4-D call
 };
 
@@ -277,7 +278,10 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr
 #pragma unroll
                     for (int j = 0; j < 32; ++j) s = fmaf(f[j], __ldg(e.head_w + oc * 32 + j), s);
                     s = 1.0f / (1.0f + __expf(-s));
-                    e.head_out[(((long long)hb * 3 + oc) * e.head_T + ht) * plane + (long long)y * e.Wout + x] = s;
+                    if (e.head_out_u8 != nullptr)
+                        e.head_out_u8[(((long long)n * e.Hout + y) * e.Wout + x) * 3 + oc] = (unsigned char)__fmul_rn(s, 255.0f);
+                    else
+                        e.head_out[(((long long)hb * 3 + oc) * e.head_T + ht) * plane + (long long)y * e.Wout + x] = s;
                 }
             } else if (e.out_f32) {
                 float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(e.out) + o_off + cg);

@@ -1088,10 +1088,22 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
     return W2L_OK;
 }
 
-static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, void* out0, void* out1, cudaStream_t st) {
+static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, void* out0, void* out1, cudaStream_t st,
+                    bool u8 = false) {
     for (Op& op : pl->ops) {
         switch (op.type) {
             case OP_INGEST: {
+                if (u8 && op.ingest_src == 1) {  // uint8 crops: mask + concat + /255 fused into the ingest
+                    IngestU8Params up;
+                    up.src = (const unsigned char*)in1; up.dst = op.ip.dst;
+                    up.N = op.ip.N; up.H = op.ip.H; up.W = op.ip.W; up.Cpad = op.ip.Cpad; up.Wp = op.ip.Wp; up.x_off = op.ip.x_off;
+                    const long long tot = (long long)up.N * up.H * up.W;
+                    const int blk = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
+                    if (ctx->bf16) ingest_u8_kernel<true><<<blk, 256, 0, st>>>(up);
+                    else ingest_u8_kernel<false><<<blk, 256, 0, st>>>(up);
+                    ctx->launches++;
+                    break;
+                }
                 IngestParams ip = op.ip;
                 ip.src = (const float*)(op.ingest_src == 0 ? in0 : in1);
                 const long long total = (long long)ip.N * ip.H * ip.W;
@@ -1102,7 +1114,10 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                 break;
             }
             case OP_CONV: {
-                if (op.head) { op.cp.ep.head_out = (float*)out0; op.hp.ep.head_out = (float*)out0; }
+                if (op.head) {
+                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.hp.ep.head_out = op.cp.ep.head_out;
+                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.hp.ep.head_out_u8 = op.cp.ep.head_out_u8;
+                }
                 CKR(launch_conv(ctx, op, st));
                 break;
             }
@@ -1417,6 +1432,51 @@ int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_h, const float* fa
     return W2L_OK;
 }
 
+int w2l_generator_forward_u8(w2l_ctx* ctx, const float* mel, const uint8_t* faces, uint8_t* out, int N, void* stream) {
+    if (!ctx || !mel || !faces || !out) return fail(W2L_EINVAL, "null argument");
+    if (N <= 0) return fail(W2L_EINVAL, "bad batch %d", N);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_GENERATOR, N, 0, &pl));
+    return run_plan(ctx, pl, mel, faces, out, nullptr, (cudaStream_t)stream, true);
+}
+
+int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_h, const uint8_t* faces_h, uint8_t* out_h, int N) {
+    if (!ctx || !mel_h || !faces_h || !out_h) return fail(W2L_EINVAL, "null argument");
+    if (N <= 0) return fail(W2L_EINVAL, "bad batch %d", N);
+    DeviceGuard g(ctx->device);
+    int nchunks = N >= 64 ? 2 : 1;
+    if (const char* ev = getenv("W2L_HOST_CHUNKS")) nchunks = std::max(1, std::min(atoi(ev), N));
+    const int cb = (N + nchunks - 1) / nchunks;
+    const size_t per_mel = 1280 * 4, per_face = 96 * 96 * 3, per_out = 96 * 96 * 3;
+    for (int i = 0; i < 2; ++i) {
+        CKR(ensure_stage(ctx, 0 + i, cb * per_mel));
+        CKR(ensure_stage(ctx, 2 + i, cb * per_face));
+        CKR(ensure_stage(ctx, 4 + i, cb * per_out));
+    }
+    int k = 0;
+    for (int b0 = 0; b0 < N; b0 += cb, ++k) {
+        const int bc = std::min(cb, N - b0);
+        const int sl = k & 1;
+        Plan* pl;
+        CKR(get_plan(ctx, W2L_NET_GENERATOR, bc, 0, &pl));
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));
+        CK(cudaMemcpyAsync(ctx->stage[0 + sl], (const char*)mel_h + b0 * per_mel, bc * per_mel, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaMemcpyAsync(ctx->stage[2 + sl], (const char*)faces_h + b0 * per_face, bc * per_face, cudaMemcpyHostToDevice, ctx->s_h2d));
+        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_h2d));
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
+        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
+        CKR(run_plan(ctx, pl, ctx->stage[0 + sl], ctx->stage[2 + sl], ctx->stage[4 + sl], nullptr, ctx->stream, true));
+        CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
+        CK(cudaMemcpyAsync((char*)out_h + b0 * per_out, ctx->stage[4 + sl], bc * per_out, cudaMemcpyDeviceToHost, ctx->s_d2h));
+        CK(cudaEventRecord(ctx->ev_out[sl], ctx->s_d2h));
+    }
+    CK(cudaStreamSynchronize(ctx->s_d2h));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return W2L_OK;
+}
+
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float* a_emb, float* v_emb, int B, void* stream) {
     if (!ctx || !mel || !face || !a_emb || !v_emb) return fail(W2L_EINVAL, "null argument");
     if (B <= 0) return fail(W2L_EINVAL, "bad batch %d", B);
@@ -1544,6 +1604,27 @@ int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_h, int64_t n_samples,
     return W2L_OK;
 }
 
+int64_t w2l_mel_num_chunks(int64_t n_frames, double fps) {
+    if (n_frames < 16 || !(fps > 0)) return 0;
+    const double mult = 80.0 / fps;  // inference.py:232
+    int64_t i = 0;
+    while ((int64_t)((double)i * mult) + 16 <= n_frames) ++i;  // :235-239: the first i that overruns becomes the last chunk
+    return i + 1;
+}
+
+int w2l_mel_chunks(w2l_ctx* ctx, const float* mel, int64_t n_frames, double fps, float* chunks, int64_t n_chunks, void* stream) {
+    if (!ctx || !mel || !chunks) return fail(W2L_EINVAL, "null argument");
+    if (n_frames < 16) return fail(W2L_EINVAL, "mel shorter than one 16-frame chunk");
+    if (n_chunks != w2l_mel_num_chunks(n_frames, fps)) return fail(W2L_EINVAL, "n_chunks %lld does not match w2l_mel_num_chunks = %lld", (long long)n_chunks, (long long)w2l_mel_num_chunks(n_frames, fps));
+    DeviceGuard g(ctx->device);
+    const long long total = (long long)n_chunks * 1280;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    mel_chunk_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, n_frames, 80.0 / fps, (int)n_chunks, chunks);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
 int64_t w2l_launch_count(const w2l_ctx* ctx) { return ctx ? ctx->launches : 0; }
 
 int64_t w2l_device_bytes(const w2l_ctx* ctx) {
@@ -1566,7 +1647,7 @@ int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, d
     int k = 0;
     for (Op& op : pl->ops) {
         if (op.type != OP_CONV || k >= cap) continue;
-        if (op.head && op.cp.ep.head_out == nullptr && op.hp.ep.head_out == nullptr) continue;
+        if (op.head && op.cp.ep.head_out == nullptr && op.hp.ep.head_out == nullptr && op.cp.ep.head_out_u8 == nullptr) continue;
         CKR(launch_conv(ctx, op, st));  // warm
         CK(cudaEventRecord(e0, st));
         for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st));

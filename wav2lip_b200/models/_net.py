@@ -47,8 +47,28 @@ class NativeNet(nn.Module):
                 "wav2lip_b200 has no CPU fallback.")
         return ref.device.index if ref.device.index is not None else torch.cuda.current_device()
 
+    # --- change detection: cheap per call (the forward itself is ~2 ms at N=128) --------------------
+    def _apply(self, fn, *args, **kwargs):  # .to() / .cuda() / .half() ... replace tensors
+        out = super()._apply(fn, *args, **kwargs)
+        self._w2l_tensors = None
+        return out
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self._w2l_tensors = None
+        return out
+
+    def mark_weights_dirty(self):
+        """Call after mutating parameters behind autograd's back (e.g. through `.data`)."""
+        self._w2l_tensors = None
+
     def _weights_key(self):
-        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+        ts = getattr(self, "_w2l_tensors", None)
+        if ts is None:
+            ts = [t for t in self.state_dict(keep_vars=True).values()]
+            self._w2l_tensors = ts
+            self._w2l_key = None
+        return tuple(t._version for t in ts)
 
     def _ensure(self, ref: torch.Tensor):
         if self.training and self.NET != _lib.NET_DISC:

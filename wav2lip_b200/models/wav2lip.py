@@ -42,6 +42,25 @@ class Wav2Lip(NativeNet):
         return out
 
 
+    def infer_u8(self, mel_batch, face_crops_u8):
+        """The inner loop of inference.py with the batch assembly fused in (scope row f):
+        mel_batch (N,1,80,16) float, face_crops_u8 (N,96,96,3) uint8 BGR crops already resized to 96x96
+        (inference.py:126) -> (N,96,96,3) uint8 BGR predictions, i.e. `p.astype(np.uint8)` of inference.py:269.
+        Equivalent to inference.py:134-140 + :259-265 on the GPU."""
+        ctx = self._ensure(face_crops_u8)
+        if face_crops_u8.dtype != torch.uint8 or face_crops_u8.dim() != 4 or tuple(face_crops_u8.shape[1:]) != (96, 96, 3):
+            raise ValueError(f"expected uint8 (N,96,96,3) crops, got {face_crops_u8.dtype} {tuple(face_crops_u8.shape)}")
+        N = face_crops_u8.shape[0]
+        mel = self._in(mel_batch)
+        if tuple(mel.shape) != (N, 1, 80, 16):
+            raise ValueError(f"expected mel (N,1,80,16), got {tuple(mel.shape)}")
+        faces = face_crops_u8.contiguous()
+        out = torch.empty((N, 96, 96, 3), device=faces.device, dtype=torch.uint8)
+        stream = torch.cuda.current_stream(faces.device).cuda_stream
+        _lib.check(ctx.lib.w2l_generator_forward_u8(ctx.h, self._p(mel), self._p(faces), self._p(out), N, C.c_void_p(stream)))
+        return out
+
+
 class Wav2Lip_disc_qual(NativeNet):
     """wav2lip.py:127-184.  forward((B,3,T,96,96)) -> (B*T, 1), rows t-major."""
     NET = _lib.NET_DISC
