@@ -1,0 +1,22 @@
+"""Small forward of every entry point, for compute-sanitizer (memcheck) on the GPU box. Test infrastructure."""
+import os, sys
+import numpy as np
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from wav2lip_b200 import audio
+from wav2lip_b200.models import SyncNet_color, Wav2Lip, Wav2Lip_disc_qual
+
+torch.manual_seed(0)
+with torch.no_grad():
+    g = Wav2Lip().cuda().eval()
+    y = g(torch.rand(3, 1, 80, 16).cuda(), torch.rand(3, 6, 96, 96).cuda())
+    y5 = g(torch.rand(2, 2, 1, 80, 16).cuda(), torch.rand(2, 6, 2, 96, 96).cuda())
+    u = g.infer_u8(torch.rand(3, 1, 80, 16).cuda(), torch.randint(0, 256, (3, 96, 96, 3), dtype=torch.uint8).cuda())
+    s = SyncNet_color().cuda().eval()
+    a, v = s(torch.rand(3, 1, 80, 16).cuda(), torch.rand(3, 15, 48, 96).cuda())
+    d = Wav2Lip_disc_qual().cuda().eval()
+    p = d(torch.rand(2, 3, 2, 96, 96).cuda())
+    m = audio.melspectrogram(np.random.randn(5000).astype(np.float32))
+    c = audio.mel_chunks(m, 25.0)
+    torch.cuda.synchronize()
+print("ok", y.shape, y5.shape, u.shape, a.shape, p.shape, m.shape, c.shape, float(y.mean()), float(p.mean()))
