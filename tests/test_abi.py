@@ -100,6 +100,20 @@ def test_missing_library_fails_loudly(lib, monkeypatch, tmp_path):
     assert "RAISED True" in out.stdout, out.stdout + out.stderr
 
 
+def test_drop_in_shadowing_of_reference_packages(lib):
+    """with <repo>/wav2lip_b200 first on sys.path the bare-name imports of the reference
+    scripts (inference.py:3,8; wav2lip_train.py:4-5; color_syncnet_train.py:4) resolve to the mirrors."""
+    code = ("from models import Wav2Lip, Wav2Lip_disc_qual\n"
+            "from models import SyncNet_color as SyncNet\n"
+            "import audio\n"
+            "m = Wav2Lip()\n"
+            "print(len(m.state_dict()), len(SyncNet().state_dict()), audio.num_frames(16000), audio.melspectrogram.__module__)\n")
+    env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "wav2lip_b200"))
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, cwd="/tmp")
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.split()[:3] == ["352", "217", "81"], out.stdout
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "wav2lip_b200")
     for dirpath, _dirs, files in os.walk(pkg):
