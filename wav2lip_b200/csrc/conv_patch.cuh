@@ -1,4 +1,4 @@
-// conv_halo.cuh — "patch" variant of the implicit-GEMM conv for layers with few channels, where the generic
+// conv_patch.cuh — "patch" variant of the implicit-GEMM conv for layers with few channels, where the generic
 // kernel (conv_tcgen05.cuh) is bound by L2->SM operand traffic because it re-loads the input box for every
 // filter tap (profiles/r1_v1_ncu_full_conv_summary.txt).  Used for
 //   * 3x3 / stride 1 / pad 1 blocks with Cout <= 64 (conv.py:5-19 at wav2lip.py:16-22,40-45,79-83; the
@@ -34,15 +34,17 @@
 
 namespace w2l {
 
-constexpr int kHaloW = 8, kHaloH = 16;  // output tile (pixels)
-constexpr int kHaloThreads = 384;       // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue A, 8-11 epilogue B
-constexpr int kHaloMaxTaps = 9;
-constexpr int kHaloMaxStages = 8;
+constexpr int kPatchTileW = 8, kPatchTileH = 16;  // output tile (pixels)
+constexpr int kPatchThreads = 384;       // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 epilogue A, 8-11 epilogue B
+constexpr int kPatchMaxTaps = 9;
+constexpr int kPatchMaxStages = 8;
 
-struct alignas(64) HaloParams {
+struct alignas(64) PatchParams {
     CUtensorMap tmA;  // activations (C, W, H, N), box (BK, PW, PH, 1)
     CUtensorMap tmB;  // weights (Cin_pad, Cout_pad, taps), box (BK, BN, 1)
     CUtensorMap tmO;  // output channel slice (BN, Wl, Hl, N) with the launch's pixel strides, box (BN, 8, 16, 1)
+    CUtensorMap tmO2; // optional second destination of the same tile (a dense zero-bordered copy for a folded consumer)
+    int has_out2;
     int tiles_x, tiles_y;   // tiles per image
     int kc;                 // channel chunks of BK
     int stages;             // depth of the patch ring
@@ -51,7 +53,7 @@ struct alignas(64) HaloParams {
     int ntaps;
     int patch_bytes;        // PW*PH*BK*2 (TMA transaction size)
     int patch_stride;       // ring slot size (patch_bytes rounded up to 1024)
-    int tap_row[kHaloMaxTaps];  // first patch row (pixel index) of each tap's view
+    int tap_row[kPatchMaxTaps];  // first patch row (pixel index) of each tap's view
     int pair;               // 1: process two tiles at a time on two accumulators (needs a ring of >= 4 patches)
     int res_row;            // >= 0: the residual IS the block input: patch row of the tile's first pixel (centre tap)
     EpiParams ep;
@@ -60,7 +62,7 @@ struct alignas(64) HaloParams {
 };
 
 template <int BN, int BK, bool kBF16, bool kHead>
-__global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __grid_constant__ HaloParams p) {
+__global__ void __launch_bounds__(kPatchThreads, 1) conv_patch_kernel(const __grid_constant__ PatchParams p) {
     constexpr int kSlab = BN * BK * 2;  // one (tap, chunk) weight slab
     constexpr int kRowBytes = BK * 2;
     constexpr int kTmemCols = (4 * BN <= 32) ? 32 : (4 * BN <= 64) ? 64 : (4 * BN <= 128) ? 128 : 256;  // 2 tiles in flight x 2 stages
@@ -78,11 +80,11 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
     constexpr uint32_t kStgBytes = ((kTileM * BN * 2 + 1023) / 1024) * 1024;                  // one staging tile per group
     const uint32_t bar_base = stg_base + 2u * kStgBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (kHaloMaxStages + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kHaloMaxStages + a); };       // 4 accumulator slots
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kHaloMaxStages + 4 + a); };
-    const uint32_t w_bar = bar_base + 8u * (2 * kHaloMaxStages + 8);
-    const uint32_t tmem_slot = bar_base + 8u * (2 * kHaloMaxStages + 9);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (kPatchMaxStages + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kPatchMaxStages + a); };       // 4 accumulator slots
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kPatchMaxStages + 4 + a); };
+    const uint32_t w_bar = bar_base + 8u * (2 * kPatchMaxStages + 8);
+    const uint32_t tmem_slot = bar_base + 8u * (2 * kPatchMaxStages + 9);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -91,6 +93,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
         tma_prefetch_desc(&p.tmA);
         tma_prefetch_desc(&p.tmB);
         tma_prefetch_desc(&p.tmO);
+        if (p.has_out2) tma_prefetch_desc(&p.tmO2);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < stages; ++s) {
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
                 mbar_arrive_expect_tx(full_bar(stage), static_cast<uint32_t>(kc) * p.patch_bytes);
                 for (int c = 0; c < kc; ++c)
                     tma_load_4d(a_base + (stage * kc + c) * p.patch_stride, &p.tmA, full_bar(stage), c * BK,
-                                tx * kHaloW + p.ox, ty * kHaloH + p.oy, n);
+                                tx * kPatchTileW + p.ox, ty * kPatchTileH + p.oy, n);
                 if (++stage == stages) { stage = 0; phase ^= 1u; }
             }
         }
@@ -143,9 +146,9 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
         constexpr uint32_t kLayout = (BK == 64) ? 2u : (BK == 32) ? 4u : 6u;
         const uint32_t a_hi = ((static_cast<uint32_t>(p.PW) * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29);
         constexpr uint32_t b_hi = ((8u * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29);
-        uint32_t tap_off[kHaloMaxTaps];
+        uint32_t tap_off[kPatchMaxTaps];
 #pragma unroll
-        for (int t = 0; t < kHaloMaxTaps; ++t) tap_off[t] = (t < ntaps ? p.tap_row[t] : 0) * kRowBytes;
+        for (int t = 0; t < kPatchMaxTaps; ++t) tap_off[t] = (t < ntaps ? p.tap_row[t] : 0) * kRowBytes;
         mbar_wait(w_bar, 0);
         // Dependent MMAs on ONE accumulator issue only every ~90 cycles whatever N is (measured: 85-110 cycles per
         // M=128,K=16 instruction for N = 16..64), so two tiles are processed together and their MMAs alternate
@@ -176,7 +179,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
                     const uint32_t patch_a = a_base + (stage_a * kc + c) * p.patch_stride;
                     const uint32_t patch_b = a_base + (stage_b * kc + c) * p.patch_stride;
 #pragma unroll
-                    for (int tap = 0; tap < kHaloMaxTaps; ++tap) {
+                    for (int tap = 0; tap < kPatchMaxTaps; ++tap) {
                         if (tap < ntaps) {
                             const uint32_t a_lo = ((patch_a + tap_off[tap]) >> 4) | 0x10000u;
                             const uint32_t a2_lo = ((patch_b + tap_off[tap]) >> 4) | 0x10000u;
@@ -225,7 +228,7 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
             const int n = tile / tiles_per_img;
             const int r = tile - n * tiles_per_img;
             const int ty = r / p.tiles_x, tx = r - ty * p.tiles_x;
-            const int x = tx * kHaloW + px, y = ty * kHaloH + py;
+            const int x = tx * kPatchTileW + px, y = ty * kPatchTileH + py;
 
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
@@ -301,8 +304,12 @@ __global__ void __launch_bounds__(kHaloThreads, 1) conv_patch_kernel(const __gri
                 asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
                 if (leader) {
                     asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-                                 ::"l"(reinterpret_cast<uint64_t>(&p.tmO)), "r"(stg), "r"(0), "r"(tx * kHaloW), "r"(ty * kHaloH), "r"(n)
+                                 ::"l"(reinterpret_cast<uint64_t>(&p.tmO)), "r"(stg), "r"(0), "r"(tx * kPatchTileW), "r"(ty * kPatchTileH), "r"(n)
                                  : "memory");
+                    if (p.has_out2)
+                        asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                                     ::"l"(reinterpret_cast<uint64_t>(&p.tmO2)), "r"(stg), "r"(0), "r"(tx * kPatchTileW), "r"(ty * kPatchTileH), "r"(n)
+                                     : "memory");
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }

@@ -10,7 +10,7 @@
 //   * a K step = one chunk of BK input channels: ONE TMA load of the (9 x 17 pixel) input patch chunk (the +1
 //     halo on the right/bottom is zero-filled at the border) and ONE 3-D TMA load of the 9 weight slabs
 //     [tap][64][BK] of that chunk;
-//   * the 9 taps of a K step are 9 shifted views of the patch (see conv_halo.cuh) feeding FOUR TMEM accumulators
+//   * the 9 taps of a K step are 9 shifted views of the patch (see conv_patch.cuh) feeding FOUR TMEM accumulators
 //     (one per output phase, 64 columns each) — consecutive MMAs hit different accumulators, which also hides the
 //     dependent-issue latency of tcgen05.mma;
 //   * two TMEM stages (2 x 4 x 64 = 512 columns) overlap the epilogue with the next unit's main loop;

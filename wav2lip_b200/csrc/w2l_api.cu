@@ -16,7 +16,7 @@
 
 #include "../../include/w2l.h"
 #include "aux_kernels.cuh"
-#include "conv_halo.cuh"
+#include "conv_patch.cuh"
 #include "conv_tcgen05.cuh"
 #include "convt_fused.cuh"
 #include "mel.cuh"
@@ -98,6 +98,8 @@ struct Act {
     bool f32 = false;
     int Wp = 0;     // row pitch in pixels (0 = W); > W only for the zero-bordered first-layer inputs
     int x_off = 0;  // left border of those inputs
+    int wstride = 1;  // folded views: pixels between consecutive windows (= the conv's horizontal stride)
+    int nwin = 0;     // folded views: number of windows per row (= output width); 0 = W
     int pitch() const { return Wp ? Wp : W; }
     uint16_t* ptr() const { return base + c_off; }
     Act slice(int off, int c) const { Act a = *this; a.c_off = c_off + off; a.C = c; return a; }
@@ -141,9 +143,9 @@ struct Op {
     bool head = false;
     int grid = 0;
     double flops = 0;  // algorithmic (true MACs*2), not padded
-    bool halo = false;  // conv_patch_kernel instead of conv_igemm_kernel
-    HaloParams hp;
-    int halo_smem = 0;
+    bool patch = false;  // conv_patch_kernel instead of conv_igemm_kernel
+    PatchParams pp;
+    int dyn_smem = 0;
     bool ctf = false;   // convt_fused_kernel
     ConvTParams tp;
     // ingest
@@ -168,10 +170,11 @@ struct w2l_ctx {
     bool bf16 = false;
     int num_sms = 148;
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
-    bool use_halo = true;   // W2L_DISABLE_HALO=1 turns the halo kernel off (A/B testing)
+    bool use_patch = true;   // W2L_DISABLE_HALO=1 turns the patch kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
     bool use_mt2 = true;    // W2L_DISABLE_MT2=1
     bool use_tma_epi = true;  // W2L_DISABLE_TMAEPI=1
+    bool use_fold_s2 = true;  // W2L_DISABLE_FOLDS2=1
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     NetW nets[3];
@@ -221,7 +224,8 @@ static int plan_act(Plan* pl, Act* a, int N, int H, int W, int C, bool f32 = fal
 static int plan_input_act(Plan* pl, Act* a, int N, int H, int W, int cin, const LayerW& lw, const Layer& L) {
     const PackedW& w = lw.ph[0];
     if (!w.fold) return plan_act(pl, a, N, H, W, ((cin + 15) / 16) * 16);
-    const int Wp = ((W + w.win - 1) + 1) / 2 * 2;
+    const int Wout = (W + 2 * L.pw - L.kw) / L.sw + 1;
+    const int Wp = (std::max(W + L.pw, (Wout - 1) * L.sw + w.win) + 1) / 2 * 2;
     void* p = nullptr;
     const size_t bytes = ((size_t)N * H * Wp * w.Cp + w.kfold) * 2;  // + one window of slack at the very end
     CKR(plan_alloc(pl, &p, bytes));
@@ -229,6 +233,7 @@ static int plan_input_act(Plan* pl, Act* a, int N, int H, int W, int cin, const 
     a->base = (uint16_t*)p;
     a->N = N; a->H = H; a->W = W; a->Cs = w.Cp; a->c_off = 0; a->C = w.kfold; a->f32 = false;
     a->Wp = Wp; a->x_off = L.pw;
+    a->wstride = L.sw; a->nwin = Wout;
     return W2L_OK;
 }
 
@@ -267,20 +272,20 @@ static ConvKernelEntry* find_conv_kernel(int BN, int BK, bool bf16, bool head, i
     return nullptr;
 }
 
-typedef void (*HaloKernelFn)(const HaloParams);
-struct HaloKernelEntry { int BN, BK; bool bf16, head; HaloKernelFn fn; bool attr_set; };
-#define W2L_HALO_ENTRY(BN_, BK_)                                                    \
+typedef void (*PatchKernelFn)(const PatchParams);
+struct PatchKernelEntry { int BN, BK; bool bf16, head; PatchKernelFn fn; bool attr_set; };
+#define W2L_PATCH_ENTRY(BN_, BK_)                                                    \
     {BN_, BK_, false, false, conv_patch_kernel<BN_, BK_, false, false>, false},    \
     {BN_, BK_, true, false, conv_patch_kernel<BN_, BK_, true, false>, false}
-static HaloKernelEntry g_halo_kernels[] = {
-    W2L_HALO_ENTRY(16, 16), W2L_HALO_ENTRY(16, 32), W2L_HALO_ENTRY(16, 64),
-    W2L_HALO_ENTRY(32, 16), W2L_HALO_ENTRY(32, 32), W2L_HALO_ENTRY(32, 64),
-    W2L_HALO_ENTRY(64, 16), W2L_HALO_ENTRY(64, 32), W2L_HALO_ENTRY(64, 64),
+static PatchKernelEntry g_patch_kernels[] = {
+    W2L_PATCH_ENTRY(16, 16), W2L_PATCH_ENTRY(16, 32), W2L_PATCH_ENTRY(16, 64),
+    W2L_PATCH_ENTRY(32, 16), W2L_PATCH_ENTRY(32, 32), W2L_PATCH_ENTRY(32, 64),
+    W2L_PATCH_ENTRY(64, 16), W2L_PATCH_ENTRY(64, 32), W2L_PATCH_ENTRY(64, 64),
     {32, 16, false, true, conv_patch_kernel<32, 16, false, true>, false},
     {32, 16, true, true, conv_patch_kernel<32, 16, true, true>, false},
 };
-static HaloKernelEntry* find_halo_kernel(int BN, int BK, bool bf16, bool head) {
-    for (auto& e : g_halo_kernels)
+static PatchKernelEntry* find_patch_kernel(int BN, int BK, bool bf16, bool head) {
+    for (auto& e : g_patch_kernels)
         if (e.BN == BN && e.BK == BK && e.bf16 == bf16 && e.head == head) return &e;
     return nullptr;
 }
@@ -302,18 +307,18 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
             CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemMax));
             e->attr_set = true;
         }
-        e->fn<<<op.grid, kCtThreads, op.halo_smem, st>>>(op.tp);
+        e->fn<<<op.grid, kCtThreads, op.dyn_smem, st>>>(op.tp);
         ctx->launches++;
         return W2L_OK;
     }
-    if (op.halo) {
-        HaloKernelEntry* e = find_halo_kernel(op.BN, op.BK, ctx->bf16, op.head);
-        if (!e) return fail(W2L_EINVAL, "no halo kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
+    if (op.patch) {
+        PatchKernelEntry* e = find_patch_kernel(op.BN, op.BK, ctx->bf16, op.head);
+        if (!e) return fail(W2L_EINVAL, "no patch kernel for BN=%d BK=%d head=%d", op.BN, op.BK, (int)op.head);
         if (!e->attr_set) {
             CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kSmemExtra));
             e->attr_set = true;
         }
-        e->fn<<<op.grid, kHaloThreads, op.halo_smem, st>>>(op.hp);
+        e->fn<<<op.grid, kPatchThreads, op.dyn_smem, st>>>(op.pp);
         ctx->launches++;
         return W2L_OK;
     }
@@ -406,8 +411,8 @@ static int encode_act_map(w2l_ctx* ctx, CUtensorMap* tm, const Act& in, int BK, 
     EncodeTiledFn enc = get_encode_fn();
     const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)in.W, (cuuint64_t)in.H, (cuuint64_t)in.N};
-    cuuint64_t strides[3] = {(cuuint64_t)in.Cs * 2, (cuuint64_t)in.pitch() * in.Cs * 2, (cuuint64_t)in.H * in.pitch() * in.Cs * 2};
+    cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)(in.nwin ? in.nwin : in.W), (cuuint64_t)in.H, (cuuint64_t)in.N};
+    cuuint64_t strides[3] = {(cuuint64_t)in.Cs * in.wstride * 2, (cuuint64_t)in.pitch() * in.Cs * 2, (cuuint64_t)in.H * in.pitch() * in.Cs * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
     cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
     CUresult r = enc(tm, dt, 4, in.ptr(), dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -432,19 +437,19 @@ static int encode_w_map(w2l_ctx* ctx, CUtensorMap* tm, const PackedW& w, int BK,
     return W2L_OK;
 }
 
-// Few-channel stride-1 layers: one input patch per tile + resident weights (conv_halo.cuh)
+// Few-channel stride-1 layers: one input patch per tile + resident weights (conv_patch.cuh)
 struct PatchGeom { int ox, oy, PW, PH, BK, patch_bytes, patch_stride, wbytes, stg_bytes, res_tap; };
 
 static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) {
-    if (!ctx->use_halo) return false;
+    if (!ctx->use_patch) return false;
     const PackedW& w = *a.w;
-    if (a.sx != 1 || a.sy != 1 || w.ntaps > kHaloMaxTaps) return false;
+    if (a.sx != 1 || a.sy != 1 || w.ntaps > kPatchMaxTaps) return false;
     if (a.cout != 16 && a.cout != 32 && a.cout != 64) return false;
     if (w.cout_pad != a.cout) return false;
     if (a.head && a.cout != 32) return false;
-    if (a.Wl < kHaloW || a.Hl < kHaloW) return false;
+    if (a.Wl < kPatchTileW || a.Hl < kPatchTileW) return false;
     if (a.out.f32) return false;
-    const double tiles = (double)((a.Wl + kHaloW - 1) / kHaloW) * ((a.Hl + kHaloH - 1) / kHaloH);
+    const double tiles = (double)((a.Wl + kPatchTileW - 1) / kPatchTileW) * ((a.Hl + kPatchTileH - 1) / kPatchTileH);
     if ((double)a.Wl * a.Hl / (tiles * kTileM) < 0.6) return false;
     int mnx = 127, mxx = -127, mny = 127, mxy = -127;
     for (int t = 0; t < w.ntaps; ++t) {
@@ -452,7 +457,7 @@ static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) 
         mny = std::min(mny, (int)w.dy[t]); mxy = std::max(mxy, (int)w.dy[t]);
     }
     g->ox = mnx; g->oy = mny;
-    g->PW = kHaloW + (mxx - mnx); g->PH = kHaloH + (mxy - mny);
+    g->PW = kPatchTileW + (mxx - mnx); g->PH = kPatchTileH + (mxy - mny);
     g->BK = pick_bk(w.cin_pad);
     g->patch_bytes = g->PW * g->PH * g->BK * 2;
     g->patch_stride = (g->patch_bytes + 1023) / 1024 * 1024;
@@ -473,29 +478,29 @@ static bool patch_eligible(const w2l_ctx* ctx, const ConvArgs& a, PatchGeom* g) 
     return true;
 }
 
-static int make_halo_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchGeom& g) {
+static int make_patch_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchGeom& g) {
     Op op;
     op.type = OP_CONV;
     op.name = a.name + (a.w->fold ? " [fold+patch]" : " [patch]");
-    op.halo = true;
+    op.patch = true;
     op.head = a.head;
     const PackedW& w = *a.w;
     const int BK = g.BK, BN = a.cout;
     op.BN = BN; op.BK = BK;
-    HaloParams& h = op.hp;
+    PatchParams& h = op.pp;
     memset(&h, 0, sizeof(h));
     CKR(encode_act_map(ctx, &h.tmA, a.in, BK, g.PW, g.PH, 1, 1, 1, a.name.c_str()));
     CKR(encode_w_map(ctx, &h.tmB, w, BK, BN, a.name.c_str()));
-    h.tiles_x = (a.Wl + kHaloW - 1) / kHaloW;
-    h.tiles_y = (a.Hl + kHaloH - 1) / kHaloH;
+    h.tiles_x = (a.Wl + kPatchTileW - 1) / kPatchTileW;
+    h.tiles_y = (a.Hl + kPatchTileH - 1) / kPatchTileH;
     h.kc = w.cin_pad / BK;
     h.PW = g.PW; h.PH = g.PH; h.ox = g.ox; h.oy = g.oy;
     h.ntaps = w.ntaps;
     h.patch_bytes = g.patch_bytes; h.patch_stride = g.patch_stride;
     for (int t = 0; t < w.ntaps; ++t) h.tap_row[t] = (w.dy[t] - g.oy) * g.PW + (w.dx[t] - g.ox);
-    h.stages = std::min(kHaloMaxStages, (kSmemBudget - g.wbytes - g.stg_bytes) / (h.kc * g.patch_stride));
-    op.halo_smem = g.wbytes + h.stages * h.kc * g.patch_stride + g.stg_bytes + kSmemExtra;
-    if (op.halo_smem > kSmemBudget + kSmemExtra || h.stages < 2) return fail(W2L_EINVAL, "%s: patch kernel smem plan %d B / %d stages", a.name.c_str(), op.halo_smem, h.stages);
+    h.stages = std::min(kPatchMaxStages, (kSmemBudget - g.wbytes - g.stg_bytes) / (h.kc * g.patch_stride));
+    op.dyn_smem = g.wbytes + h.stages * h.kc * g.patch_stride + g.stg_bytes + kSmemExtra;
+    if (op.dyn_smem > kSmemBudget + kSmemExtra || h.stages < 2) return fail(W2L_EINVAL, "%s: patch kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
     fill_epi(&h.ep, a);
     h.res_row = g.res_tap >= 0 ? h.tap_row[g.res_tap] : -1;
     h.pair = h.stages >= 4 ? 1 : 0;
@@ -507,7 +512,7 @@ static int make_halo_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchGe
         const CUtensorMapSwizzle sw = BN == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BN == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
         cuuint64_t dims[4] = {(cuuint64_t)BN, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
         cuuint64_t strides[3] = {(cuuint64_t)h.ep.out_sx * 2, (cuuint64_t)h.ep.out_sy * 2, (cuuint64_t)h.ep.out_sn * 2};
-        cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)kHaloW, (cuuint32_t)kHaloH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)BN, (cuuint32_t)kPatchTileW, (cuuint32_t)kPatchTileH, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
         if (a.out.f32) return fail(W2L_EINVAL, "%s: patch kernel stores 16-bit outputs only", a.name.c_str());
         CUresult r = enc(&h.tmO, dt, 4, h.ep.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
@@ -537,7 +542,7 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     if (a.in.C != w.cin_pad) return fail(W2L_EINVAL, "%s: input view has %d channels, weights packed for %d", a.name.c_str(), a.in.C, w.cin_pad);
     if (a.cout % 16 != 0) return fail(W2L_EINVAL, "%s: cout %d not a multiple of 16", a.name.c_str(), a.cout);
     PatchGeom geom;
-    if (patch_eligible(ctx, a, &geom)) return make_halo_op(ctx, pl, a, geom);
+    if (patch_eligible(ctx, a, &geom)) return make_patch_op(ctx, pl, a, geom);
     Op op;
     op.type = OP_CONV;
     op.name = a.name + (w.fold ? " [fold]" : "");
@@ -652,7 +657,7 @@ static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const Lay
     const int fixed = 2 * kTileM * kCtBN * 2 + kSmemExtra;
     t.stages = std::min(kCtMaxStages, (kCtSmemMax - fixed) / stage_bytes);
     if (t.stages < 2) return fail(W2L_EINVAL, "%s: fused convT does not fit shared memory", L.name.c_str());
-    op.halo_smem = t.stages * stage_bytes + fixed;
+    op.dyn_smem = t.stages * stage_bytes + fixed;
     t.act = ACT_RELU;
     for (int r = 0; r < 3; ++r)
         for (int s2 = 0; s2 < 3; ++s2) {
@@ -672,9 +677,8 @@ static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const Lay
 }
 
 // Emit the launches of one block (conv / convT) of a spec table.
-static int emit_block(w2l_ctx* ctx, Plan* pl, int net, int li, const Layer& L, const Act& in, const Act& out,
+static int emit_block(w2l_ctx* ctx, Plan* pl, const NetW& nw, int li, const Layer& L, const Act& in, const Act& out,
                       const Act* res, bool head = false, int head_B = 1, int head_T = 1) {
-    const NetW& nw = ctx->nets[net];
     const LayerW& lw = nw.layers[li];
     ConvArgs a;
     a.in = in; a.out = out; a.res = res;
@@ -685,7 +689,7 @@ static int emit_block(w2l_ctx* ctx, Plan* pl, int net, int li, const Layer& L, c
     if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
         a.name = L.name;
         a.w = &lw.ph[0];
-        a.sx = L.sw; a.sy = L.sh;
+        a.sx = lw.ph[0].fold ? 1 : L.sw; a.sy = L.sh;  // folded first layers: the tensor map already strides the windows
         a.Hl = out.H; a.Wl = out.W;
         a.macs_per_pixel = (double)L.cin * L.cout * L.kh * L.kw;
         return make_conv_op(ctx, pl, a);
@@ -793,7 +797,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
     free_layer(*lw);
     const int pad_to = 16;
     int reps = 1;
-    if (first_layer && ctx->use_fold && L.kind != W2L_BLOCK_CONVT_BN_RELU && L.cin <= 16 && L.kw >= 3 && L.sw == 1) {
+    if (first_layer && ctx->use_fold && L.kind != W2L_BLOCK_CONVT_BN_RELU && L.cin <= 16 && L.kw >= 3 && (L.sw == 1 || L.sw == 2)) {
         // tiny-Cin first layer: fold the kw horizontal taps into K (one K row per filter row r)
         PackedW pw;
         pw.fold = true;
@@ -962,7 +966,7 @@ static int emit_chain(w2l_ctx* ctx, Plan* pl, int net, const std::vector<Layer>&
         } else {
             CKR(tmp_act(ctx, pl, tp, &out, x.N, Ho, Wo, L.cout, x.base));
         }
-        CKR(emit_block(ctx, pl, net, idx[k], L, x, out, L.residual ? &x : nullptr));
+        CKR(emit_block(ctx, pl, ctx->nets[net], idx[k], L, x, out, L.residual ? &x : nullptr));
         pl->layer_out[idx[k]] = out;
         x = out;
     }
@@ -1003,6 +1007,28 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     for (int i = 0; i < 7; ++i) {
         Act dst = D[6 - i].slice(dec_c[6 - i], skip_c[6 - i]);
         CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.face_enc[i], x, &tpe, &dst, &x));
+        if (i == 0 && nw.layers[g.face_enc[1][0]].ph[0].fold) {
+            // The 16->32 stride-2 block gathers every other pixel of a 16-channel slice of D[6]: 32-byte TMA rows, the
+            // slowest layer per FLOP. Give it a dense zero-bordered copy of the first block's output instead (second
+            // TMA store of the same staged tile), read through the overlapping-window map with the 3 horizontal taps
+            // folded into K.
+            Op& prev = pl->ops.back();
+            if (!prev.patch || prev.head) return fail(W2L_ESTATE, "folded stride-2 block needs the patch kernel on the first block");
+            const Layer& L1 = g.layers[g.face_enc[1][0]];
+            Act e0;
+            CKR(plan_input_act(pl, &e0, N, 96, 96, L1.cin, nw.layers[g.face_enc[1][0]], L1));
+            EncodeTiledFn enc = get_encode_fn();
+            const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+            cuuint64_t od[4] = {16, 96, 96, (cuuint64_t)N};
+            cuuint64_t os[3] = {(cuuint64_t)e0.Cs * 2, (cuuint64_t)e0.Wp * e0.Cs * 2, (cuuint64_t)96 * e0.Wp * e0.Cs * 2};
+            cuuint32_t ob[4] = {16, (cuuint32_t)kPatchTileW, (cuuint32_t)kPatchTileH, 1};
+            cuuint32_t oe[4] = {1, 1, 1, 1};
+            CUresult r = enc(&prev.pp.tmO2, dt, 4, e0.base + (size_t)e0.x_off * e0.Cs, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                             CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "cuTensorMapEncodeTiled(dense copy) failed with %d", (int)r);
+            prev.pp.has_out2 = 1;
+            x = e0;
+        }
     }
     // decoder
     TmpPool tpd;
@@ -1016,7 +1042,7 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     const Layer& L = g.layers[g.output_block0];
     Act none;
     none.N = N; none.H = 96; none.W = 96; none.Cs = 32; none.C = 32;
-    CKR(emit_block(ctx, pl, W2L_NET_GENERATOR, g.output_block0, L, x, none, nullptr, true, T > 0 ? B : N, T > 0 ? T : 1));
+    CKR(emit_block(ctx, pl, ctx->nets[W2L_NET_GENERATOR], g.output_block0, L, x, none, nullptr, true, T > 0 ? B : N, T > 0 ? T : 1));
     return W2L_OK;
 }
 
@@ -1115,8 +1141,8 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
             }
             case OP_CONV: {
                 if (op.head) {
-                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.hp.ep.head_out = op.cp.ep.head_out;
-                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.hp.ep.head_out_u8 = op.cp.ep.head_out_u8;
+                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.pp.ep.head_out = op.cp.ep.head_out;
+                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.pp.ep.head_out_u8 = op.cp.ep.head_out_u8;
                 }
                 CKR(launch_conv(ctx, op, st));
                 break;
@@ -1284,10 +1310,12 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     {
         const char* e1 = getenv("W2L_DISABLE_HALO");
         const char* e2 = getenv("W2L_DISABLE_FOLD");
-        ctx->use_halo = !(e1 && e1[0] == '1');
+        ctx->use_patch = !(e1 && e1[0] == '1');
         ctx->use_fold = !(e2 && e2[0] == '1');
         const char* e3 = getenv("W2L_DISABLE_BN256");
         ctx->use_bn256 = !(e3 && e3[0] == '1');
+        const char* e7 = getenv("W2L_DISABLE_FOLDS2");
+        ctx->use_fold_s2 = !(e7 && e7[0] == '1');
         const char* e6 = getenv("W2L_DISABLE_TMAEPI");
         ctx->use_tma_epi = !(e6 && e6[0] == '1');
         const char* e5 = getenv("W2L_DISABLE_MT2");
@@ -1361,7 +1389,10 @@ int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* na
         CKR(fetch_block_tensors(tm, L, &W, &b, &gm, &be, &m, &v));
         const bool hw1 = (net == W2L_NET_GENERATOR && L.name == "face_decoder_blocks.1.0");
         // blocks fed directly by the ingest kernel (caller tensors): the only ones with a tiny Cin
-        const bool first = L.name == "face_encoder_blocks.0.0" || L.name == "audio_encoder.0" || L.name == "face_encoder.0";
+        bool first = L.name == "face_encoder_blocks.0.0" || L.name == "audio_encoder.0" || L.name == "face_encoder.0";
+        // the generator's 16->32 stride-2 block reads a dense zero-bordered copy of the first block's output (written by
+        // the patch kernel's second TMA store) through the same overlapping-window trick
+        if (net == W2L_NET_GENERATOR && L.name == "face_encoder_blocks.1.0" && ctx->use_patch && ctx->use_fold && ctx->use_fold_s2) first = true;
         CKR(load_layer(ctx, &nw.layers[i], L, W, b, gm, be, m, v, hw1, first, st));
     }
     if (nw.head_w) { cudaFree(nw.head_w); nw.head_w = nullptr; }
@@ -1514,8 +1545,7 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     if (L.residual && (L.cin != L.cout || Ho != H || Wo != W)) return fail(W2L_EINVAL, "residual needs same shape");
     const bool saved_fold = ctx->use_fold;
     if (L.residual) ctx->use_fold = false;  // the residual is read from the block input: keep it in the plain NHWC layout
-    // a private one-block "network" in slot 3 semantics: reuse the machinery with a scratch NetW
-    NetW saved = ctx->nets[W2L_NET_DISC];  // borrow a slot; restored below
+    // a private one-block "network"
     NetW scratch;
     scratch.layers.resize(1);
     int r = load_layer(ctx, &scratch.layers[0], L, weight, bias, bn_w, bn_b, bn_m, bn_v, H == 1 && W == 1, true, st);
@@ -1526,14 +1556,12 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     if (r == W2L_OK) r = plan_act(&pl, &out, N, Ho, Wo, L.cout);
     if (r == W2L_OK) {
         add_ingest(&pl, "ingest.x", 0, in, N, L.cin, (long long)L.cin * H * W, (long long)H * W, 0, 0, W);
-        ctx->nets[W2L_NET_DISC] = scratch;
-        r = emit_block(ctx, &pl, W2L_NET_DISC, 0, L, in, out, L.residual ? &in : nullptr);
+        r = emit_block(ctx, &pl, scratch, 0, L, in, out, L.residual ? &in : nullptr);
         if (r == W2L_OK) {
             Plan* lp = ctx->last_plan[W2L_NET_DISC];
-            r = run_plan(ctx, &pl, x, nullptr, nullptr, nullptr, st);
+            r = run_plan(ctx, &pl, x, nullptr, nullptr, nullptr, st);  // (pl.net only labels the plan)
             ctx->last_plan[W2L_NET_DISC] = lp;
         }
-        ctx->nets[W2L_NET_DISC] = saved;
     }
     if (r == W2L_OK) {
         const long long total = (long long)N * L.cout * Ho * Wo;
@@ -1647,7 +1675,7 @@ int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, d
     int k = 0;
     for (Op& op : pl->ops) {
         if (op.type != OP_CONV || k >= cap) continue;
-        if (op.head && op.cp.ep.head_out == nullptr && op.hp.ep.head_out == nullptr && op.cp.ep.head_out_u8 == nullptr) continue;
+        if (op.head && op.cp.ep.head_out == nullptr && op.pp.ep.head_out == nullptr && op.cp.ep.head_out_u8 == nullptr) continue;
         CKR(launch_conv(ctx, op, st));  // warm
         CK(cudaEventRecord(e0, st));
         for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st));
