@@ -369,6 +369,14 @@ def main():
                     "share_of_step": conv_ms / ms_per_step if ms_per_step > 0 else None,
                     "whole_step_tflops": value / world * FLOP_PER_CROP / 1e12,
                     "traffic": None}
+        # DRAM bytes of the same launches from the committed ncu capture (profiles/), valid for the default workload
+        tp = os.path.join(ROOT, "profiles", "r1_final_ncu_dram_per_step.json")
+        if os.path.exists(tp) and (B, T) == (B_DEFAULT, T_DEFAULT):
+            tj = json.load(open(tp))
+            roofline["traffic"] = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+            roofline["traffic_note"] = ("dram__bytes_read+write summed over the %d conv launches of one step (ncu, profiles/"
+                                        "r1_final_ncu_dram_per_step.json); algorithmic conv in+out bytes per step = %.2f GB"
+                                        % (tj["launches"], (4.81e6 + 4.49e6) * 2 * N / 1e9))
         if args.profile_out and rank == 0:
             with open(args.profile_out, "w") as f:
                 f.write(f"# per-launch CUDA-event times, B={B} T={T} (N={N}), {len(prof)} conv launches, sum {conv_ms:.3f} ms\n")
