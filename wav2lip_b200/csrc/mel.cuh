@@ -33,7 +33,8 @@ struct MelParams {
     long long L;
     float* mel;          // (80, F) row-major
     long long F;
-    const double2* tw;   // exp(-2 pi i m / 800), m in [0, 800)
+    const double2* tw;   // [0,401): exp(-2 pi i m / 800) (window + real-FFT post pass); [401, 401+395): per-pass twiddles
+                         // T[r][k] = exp(-2 pi i r k / (Ns R)), r-major so that a warp reads consecutive k (no bank conflicts)
     const float* bvals;  // packed non-zero filterbank weights
     const int* boff;     // [80] offset into bvals
     const int* bstart;   // [80] first FFT bin of the band
@@ -78,16 +79,23 @@ __device__ __forceinline__ void butterfly<5>(double2* v) {
     v[3] = make_double2(t2.x - u2.y, t2.y + u2.x);
 }
 
+// Twiddle table layout in shared memory (double2 units)
+constexpr int MEL_TW_POST = 0;                 // 401 entries
+constexpr int MEL_TW_P2 = 401;                 // radix 5, Ns = 5  : T[r-1][k], r = 1..4, k < 5    (20)
+constexpr int MEL_TW_P3 = MEL_TW_P2 + 20;      // radix 4, Ns = 25 : T[r-1][k], r = 1..3, k < 25   (75)
+constexpr int MEL_TW_P4 = MEL_TW_P3 + 75;      // radix 4, Ns = 100: T[r-1][k], r = 1..3, k < 100  (300)
+constexpr int MEL_TW_TOTAL = MEL_TW_P4 + 300;  // 796
+
 // One Stockham pass of a 400-point FFT: radix R, Ns = product of the radices already applied.
+// tw_pass = this pass's r-major twiddle table (nullptr for the first pass, whose twiddles are all 1).
 template <int R>
-__device__ __forceinline__ void fft400_pass(const double2* in, double2* out, int j, int Ns, const double2* tw) {
+__device__ __forceinline__ void fft400_pass(const double2* in, double2* out, int j, int Ns, const double2* tw_pass) {
     const int k = j % Ns;
-    const int tstep = k * (MEL_NFFT / (Ns * R));  // index step into the 800th-roots table
     double2 v[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         v[r] = in[j + r * (400 / R)];
-        if (r > 0) v[r] = cmul(v[r], tw[(r * tstep) % MEL_NFFT]);
+        if (r > 0 && tw_pass != nullptr) v[r] = cmul(v[r], tw_pass[(r - 1) * Ns + k]);
     }
     butterfly<R>(v);
     const int j0 = (j / Ns) * Ns * R + k;
@@ -97,8 +105,8 @@ __device__ __forceinline__ void fft400_pass(const double2* in, double2* out, int
 
 __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p) {
     extern __shared__ uint8_t mel_smem[];
-    double2* tw = reinterpret_cast<double2*>(mel_smem);                       // [800]
-    double2* bufs = tw + MEL_NFFT;                                            // [FPB][2][400]
+    double2* tw = reinterpret_cast<double2*>(mel_smem);                       // [MEL_TW_TOTAL]
+    double2* bufs = tw + MEL_TW_TOTAL;                                        // [FPB][2][400]
     float* mags = reinterpret_cast<float*>(bufs + MEL_FPB * 2 * 400);         // [FPB][404]
     float* outs = mags + MEL_FPB * 404;                                       // [80][FPB]
 
@@ -107,7 +115,7 @@ __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p
     const long long t = (long long)blockIdx.x * MEL_FPB + f;
     const bool live = t < p.F;
 
-    for (int i = threadIdx.x; i < MEL_NFFT; i += blockDim.x) tw[i] = p.tw[i];
+    for (int i = threadIdx.x; i < MEL_TW_TOTAL; i += blockDim.x) tw[i] = p.tw[i];
     __syncthreads();
 
     double2* b0 = bufs + f * 800;
@@ -126,20 +134,20 @@ __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p
                 if (j >= p.L) j = 2 * (p.L - 1) - j;
                 const double x0 = (double)__ldg(p.wav + j);
                 const double y = (j > 0) ? x0 + (-0.97) * (double)__ldg(p.wav + j - 1) : x0;
-                const double w = 0.5 - 0.5 * tw[n].x;  // periodic Hann: 0.5 - 0.5 cos(2 pi n / 800)
+                const double w = 0.5 - 0.5 * tw[n <= 400 ? n : MEL_NFFT - n].x;  // periodic Hann: 0.5 - 0.5 cos(2 pi n / 800)
                 s[e] = w * y;
             }
             b0[i] = make_double2(s[0], s[1]);
         }
     }
     __syncthreads();
-    if (live && tid < 80) fft400_pass<5>(b0, b1, tid, 1, tw);
+    if (live && tid < 80) fft400_pass<5>(b0, b1, tid, 1, nullptr);
     __syncthreads();
-    if (live && tid < 80) fft400_pass<5>(b1, b0, tid, 5, tw);
+    if (live && tid < 80) fft400_pass<5>(b1, b0, tid, 5, tw + MEL_TW_P2);
     __syncthreads();
-    if (live && tid < 100) fft400_pass<4>(b0, b1, tid, 25, tw);
+    if (live && tid < 100) fft400_pass<4>(b0, b1, tid, 25, tw + MEL_TW_P3);
     __syncthreads();
-    if (live && tid < 100) fft400_pass<4>(b1, b0, tid, 100, tw);
+    if (live && tid < 100) fft400_pass<4>(b1, b0, tid, 100, tw + MEL_TW_P4);
     __syncthreads();
     // ---- real-FFT post pass: X[k] = E[k] + W800^k O[k]; round to complex64; magnitude in fp32 ----
     if (live) {
@@ -173,6 +181,6 @@ __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p
     }
 }
 
-constexpr int kMelSmemBytes = MEL_NFFT * 16 + MEL_FPB * 800 * 16 + MEL_FPB * 404 * 4 + MEL_BANDS * MEL_FPB * 4;
+constexpr int kMelSmemBytes = MEL_TW_TOTAL * 16 + MEL_FPB * 800 * 16 + MEL_FPB * 404 * 4 + MEL_BANDS * MEL_FPB * 4;
 
 }  // namespace w2l

@@ -1198,12 +1198,22 @@ static void build_mel_basis(std::vector<float>* dense) {
 }
 
 static int init_mel_tables(w2l_ctx* ctx) {
-    std::vector<double2> tw(MEL_NFFT);
-    for (int m = 0; m < MEL_NFFT; ++m) {
-        // exact octant symmetry is not needed; long double keeps the table at double round-off
-        const long double a = -2.0L * 3.141592653589793238462643383279502884L * m / MEL_NFFT;
-        tw[m] = make_double2((double)cosl(a), (double)sinl(a));
+    std::vector<double2> tw(MEL_TW_TOTAL);
+    const long double kTwoPi = 2.0L * 3.141592653589793238462643383279502884L;
+    for (int m = 0; m <= 400; ++m) {  // post-pass / window table: exp(-2 pi i m / 800)
+        const long double a = -kTwoPi * m / MEL_NFFT;
+        tw[MEL_TW_POST + m] = make_double2((double)cosl(a), (double)sinl(a));
     }
+    auto fill_pass = [&](int base, int R, int Ns) {  // T[r-1][k] = exp(-2 pi i r k / (Ns R))
+        for (int r = 1; r < R; ++r)
+            for (int k = 0; k < Ns; ++k) {
+                const long double a = -kTwoPi * (long double)(r * k) / (long double)(Ns * R);
+                tw[base + (r - 1) * Ns + k] = make_double2((double)cosl(a), (double)sinl(a));
+            }
+    };
+    fill_pass(MEL_TW_P2, 5, 5);
+    fill_pass(MEL_TW_P3, 4, 25);
+    fill_pass(MEL_TW_P4, 4, 100);
     std::vector<float> dense;
     build_mel_basis(&dense);
     std::vector<float> vals;
