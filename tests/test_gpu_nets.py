@@ -6,7 +6,7 @@ activations are fp16 (10-bit mantissa = TF32's), accumulation, BatchNorm scale/s
 the sigmoid head are fp32.  Per block that is ~2^-11 relative; through the ~20 blocks of the longest
 path it grows to ~1.5e-3 relative on the last feature map.
   * BASELINE configs[0] ("random weights" = the reference constructor's init statistics, randomised BN):
-    north_star's bar, max|out - ref| <= 1e-3, is asserted as is (measured ~2e-5).
+    north_star's bar, max|out - ref| <= 1e-3, is asserted as is (measured 6.5e-5).
   * the "stress" weights (variance-preserving init, logits std 2.5 — far harsher than the bar's setting)
     are asserted at 8e-3 on the sigmoid output and 3e-3*max|ref| on every intermediate feature map;
     they exist so that a wrong tap, stride, phase or channel slice cannot hide behind sigmoid(~0)."""
@@ -45,7 +45,7 @@ def test_generator_default_init_meets_the_bar(golden_dir):
     assert y.shape == (2, 3, 96, 96)
     err = np.abs(y - gold["gen4_default_out"]).max()   # vs the REAL reference's output
     assert err <= BAR, err
-    assert err <= 2e-4, f"default-init error regressed: {err}"  # measured ~2e-5
+    assert err <= 2e-4, f"default-init error regressed: {err}"  # measured 6.5e-5
 
 
 def test_generator_4d_stress_vs_reference_golden(gen_stress, golden_dir):
