@@ -1,4 +1,5 @@
-// conv_tcgen05.cuh — the fused conv-block kernel of the Wav2Lip hot path for sm_100a.
+// conv_tcgen05.cuh — the generic fused conv-block kernel of the Wav2Lip hot path for sm_100a, plus the PTX
+// wrappers and the epilogue helpers shared by the specialised kernels (conv_patch.cuh, convt_fused.cuh).
 //
 // One persistent, warp-specialised kernel computes, for every block kind of
 // /root/reference/models/conv.py (Conv2d :5-19, nonorm_Conv2d :21-31 and, phase by phase,
@@ -10,20 +11,25 @@
 //     M = output pixels (a 128-row tile = a bw x bh x bn box of the NHWC output grid),
 //     N = output channels (BN per tile), K = filter taps x input channels (BK per step).
 //
-//   warp 0  : TMA producer. For each K step one 4-D tiled TMA load brings the input box of the
+//   warp 0  : TMA producer. For each K step one 4-D tiled TMA load per M tile brings the input box of the
 //             current filter tap (start coordinate = tile origin * stride + tap offset; out-of-bounds
 //             coordinates are zero-filled by the TMA unit, which IS the conv zero padding) and one
 //             3-D TMA load brings the [BN x BK] weight slice of that tap. Both land K-major with the
 //             hardware 128/64/32-byte swizzle that the UMMA shared-memory descriptors expect.
 //   warp 1  : MMA issuer. One lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
-//             accumulating in TMEM (fp32); tcgen05.commit releases smem stages / publishes the tile.
-//   warp 2  : TMEM allocator (2 accumulator stages x BN columns, so the epilogue of tile i overlaps
-//             the main loop of tile i+1).
-//   warps 4-7: epilogue. tcgen05.ld the accumulator (lane = GEMM row = output pixel), apply the folded
-//             BatchNorm scale/shift (conv bias folded in), the residual add (conv.py:16-18: after BN,
-//             before ReLU), ReLU / LeakyReLU(0.01), convert and store NHWC straight into the channel
-//             slice of the consumer's buffer (so torch.cat of wav2lip.py:108 never exists). The
-//             generator head (1x1 conv 32->3 + sigmoid, wav2lip.py:84-85) is fused for the last block.
+//             accumulating in TMEM (fp32); tcgen05.commit releases smem stages / publishes the unit.
+//             With MT=2 a CTA works on two M tiles that share every weight slab and alternates the MMAs
+//             between their accumulators (less operand traffic per FLOP, dependent-issue latency hidden).
+//   warp 2  : TMEM allocator (2 accumulator stages x MT x BN columns, so the epilogue of unit i overlaps
+//             the main loop of unit i+1).
+//   warps 4+: one epilogue group of 4 warps per M tile. tcgen05.ld the accumulator (lane = GEMM row = output
+//             pixel), apply the folded BatchNorm scale/shift (conv bias folded in), the residual add
+//             (conv.py:16-18: after BN, before ReLU), ReLU / LeakyReLU(0.01) and write NHWC 16-bit straight
+//             into the channel slice of the consumer's buffer (so torch.cat of wav2lip.py:108 never exists).
+//             Staged mode (tma_epi): the residual tile arrives by TMA into a swizzled shared-memory tile,
+//             is combined in place and leaves by ONE TMA tensor store per 64 channels (which also clips
+//             ragged tiles); direct mode (fp32 outputs, fused generator head wav2lip.py:84-85): per-thread
+//             global accesses.
 //
 // Everything a launch needs is in ConvParams (a __grid_constant__), built once per plan on the host.
 #pragma once
