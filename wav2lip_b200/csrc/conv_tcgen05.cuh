@@ -44,7 +44,7 @@ namespace w2l {
 constexpr int kTileM = 128;
 constexpr int kMaxTaps = 49;
 constexpr int kConvThreads = 256;
-constexpr int kSmemBudget = 200 * 1024;  // patch kernels: weights + patch ring + staging; barriers live in the extra KB
+constexpr int kSmemBudget = 224 * 1024;  // patch kernels: weights + patch ring + staging; barriers live in the extra KB
 constexpr int kSmemExtra = 2048;         // 1024 alignment slack + barriers
 constexpr int kSmemMax = 227 * 1024;     // dynamic shared memory limit per CTA on sm_100
 

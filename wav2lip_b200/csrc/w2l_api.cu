@@ -503,7 +503,7 @@ static int make_patch_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchG
     if (op.dyn_smem > kSmemBudget + kSmemExtra || h.stages < 2) return fail(W2L_EINVAL, "%s: patch kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
     fill_epi(&h.ep, a);
     h.res_row = g.res_tap >= 0 ? h.tap_row[g.res_tap] : -1;
-    h.pair = h.stages >= 4 ? 1 : 0;
+    h.pair = h.stages >= 3 ? 1 : 0;  // two tiles in flight + at least one being prefetched
     if (!a.head) {
         // TMA-store view of the output: the BN-channel slice, with this launch's pixel strides (transposed-conv phases
         // interleave), box = one 8 x 16 tile; out-of-range pixels of ragged tiles are clipped by the TMA unit
