@@ -163,6 +163,7 @@ struct Plan {
     std::vector<void*> allocs;
     size_t bytes = 0;
     std::map<int, Act> layer_out;  // layer index -> activation view (debug export)
+    long long last_used = 0;       // LRU stamp
 };
 
 struct w2l_ctx {
@@ -181,6 +182,7 @@ struct w2l_ctx {
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};
     int64_t launches = 0;
+    long long plan_clock = 0;
     size_t weight_bytes = 0;
     // host-buffer entry points: compute stream + copy streams, double-buffered device staging
     cudaStream_t stream = nullptr;
@@ -1095,12 +1097,23 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
     char key[64];
     snprintf(key, sizeof(key), "%d:%d:%d:%d", net, B, T, (int)ctx->keep_all);
     auto it = ctx->plans.find(key);
-    if (it != ctx->plans.end()) { *out = it->second.get(); return W2L_OK; }
+    if (it != ctx->plans.end()) { it->second->last_used = ++ctx->plan_clock; *out = it->second.get(); return W2L_OK; }
     if (!ctx->nets[net].loaded) return fail(W2L_ESTATE, "weights of net %d not loaded", net);
-    // keep at most a few plans per net alive (activation arenas are large)
-    int count = 0;
-    for (auto& kv : ctx->plans) if (kv.second->net == net) ++count;
-    if (count >= 4) drop_plans(ctx, net);
+    // keep at most a few plans per net alive (activation arenas are large): evict the least recently used
+    for (;;) {
+        int count = 0;
+        auto lru = ctx->plans.end();
+        for (auto p = ctx->plans.begin(); p != ctx->plans.end(); ++p)
+            if (p->second->net == net) {
+                ++count;
+                if (lru == ctx->plans.end() || p->second->last_used < lru->second->last_used) lru = p;
+            }
+        if (count < 6) break;
+        CK(cudaDeviceSynchronize());  // the plan's buffers may still be in use by queued launches
+        if (ctx->last_plan[net] == lru->second.get()) ctx->last_plan[net] = nullptr;
+        free_plan(lru->second.get());
+        ctx->plans.erase(lru);
+    }
     std::unique_ptr<Plan> pl(new Plan());
     pl->net = net; pl->B = B; pl->T = T;
     pl->N = (net == W2L_NET_SYNCNET) ? B : (T > 0 ? B * T : B);
@@ -1109,6 +1122,7 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
     else if (net == W2L_NET_SYNCNET) r = build_syncnet_plan(ctx, pl.get());
     else r = build_disc_plan(ctx, pl.get());
     if (r != W2L_OK) { free_plan(pl.get()); return r; }
+    pl->last_used = ++ctx->plan_clock;
     *out = pl.get();
     ctx->plans[key] = std::move(pl);
     return W2L_OK;
