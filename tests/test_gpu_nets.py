@@ -155,6 +155,27 @@ def test_generator_shape_errors(gen_stress):
         gen_stress(torch.zeros(3, 1, 80, 16).cuda(), torch.zeros(2, 6, 96, 96).cuda())
 
 
+def test_empty_and_single_item_batches(gen_stress):
+    """Edge cases: an empty batch returns an empty tensor (as torch does), a 5-D call with T=1 and B=1 works."""
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip_disc_qual
+    with torch.no_grad():
+        y0 = gen_stress(torch.zeros(0, 1, 80, 16).cuda(), torch.zeros(0, 6, 96, 96).cuda())
+        assert tuple(y0.shape) == (0, 3, 96, 96)
+        y5 = gen_stress(torch.zeros(0, 5, 1, 80, 16).cuda(), torch.zeros(0, 6, 5, 96, 96).cuda())
+        assert tuple(y5.shape) == (0, 3, 5, 96, 96)
+        mel, face = O.make_generator_inputs(1, seed=8, t=1)
+        y11 = gen_stress(mel.cuda(), face.cuda())
+        assert tuple(y11.shape) == (1, 3, 1, 96, 96)
+        y4 = gen_stress(mel[:, 0].cuda(), face[:, :, 0].cuda())
+        assert torch.equal(y11[:, :, 0], y4)
+        s = SyncNet_color().cuda().eval()
+        a, v = s(torch.zeros(0, 1, 80, 16).cuda(), torch.zeros(0, 15, 48, 96).cuda())
+        assert tuple(a.shape) == (0, 512) and tuple(v.shape) == (0, 512)
+        d = Wav2Lip_disc_qual().cuda().eval()
+        assert tuple(d(torch.zeros(0, 3, 5, 96, 96).cuda()).shape) == (0, 1)
+        assert tuple(gen_stress.infer_u8(torch.zeros(0, 1, 80, 16).cuda(), torch.zeros(0, 96, 96, 3, dtype=torch.uint8).cuda()).shape) == (0, 96, 96, 3)
+
+
 def test_syncnet_vs_reference_golden(golden_dir):
     from wav2lip_b200.models import SyncNet_color
     gold = np.load(os.path.join(golden_dir, "syncnet.npz"))

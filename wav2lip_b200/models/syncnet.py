@@ -24,6 +24,8 @@ class SyncNet_color(NativeNet):
             raise ValueError(f"expected (B,1,80,16) and (B,15,48,96), got {tuple(mel.shape)} and {tuple(face.shape)}")
         a = torch.empty((B, 512), device=face.device, dtype=torch.float32)
         v = torch.empty((B, 512), device=face.device, dtype=torch.float32)
+        if B == 0:
+            return a, v
         stream = torch.cuda.current_stream(face.device).cuda_stream
         _lib.check(ctx.lib.w2l_syncnet_forward(ctx.h, self._p(mel), self._p(face), self._p(a), self._p(v), B, C.c_void_p(stream)))
         return a, v

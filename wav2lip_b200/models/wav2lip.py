@@ -37,6 +37,8 @@ class Wav2Lip(NativeNet):
             if tuple(mel.shape) != (B, 1, 80, 16) or tuple(face.shape[1:]) != (6, 96, 96):
                 raise ValueError(f"expected (N,1,80,16) and (N,6,96,96), got {tuple(mel.shape)} and {tuple(face.shape)}")
             out = torch.empty((B, 3, 96, 96), device=face.device, dtype=torch.float32)
+        if out.numel() == 0:  # empty batch: torch returns an empty tensor, and so do we (no launch)
+            return out
         stream = torch.cuda.current_stream(face.device).cuda_stream
         _lib.check(ctx.lib.w2l_generator_forward(ctx.h, self._p(mel), self._p(face), self._p(out), B, T, C.c_void_p(stream)))
         return out
@@ -56,6 +58,8 @@ class Wav2Lip(NativeNet):
             raise ValueError(f"expected mel (N,1,80,16), got {tuple(mel.shape)}")
         faces = face_crops_u8.contiguous()
         out = torch.empty((N, 96, 96, 3), device=faces.device, dtype=torch.uint8)
+        if N == 0:
+            return out
         stream = torch.cuda.current_stream(faces.device).cuda_stream
         _lib.check(ctx.lib.w2l_generator_forward_u8(ctx.h, self._p(mel), self._p(faces), self._p(out), N, C.c_void_p(stream)))
         return out
@@ -84,6 +88,8 @@ class Wav2Lip_disc_qual(NativeNet):
             raise ValueError(f"expected (B,3,T,96,96), got {tuple(x.shape)}")
         B, T = x.shape[0], x.shape[2]
         out = torch.empty((B * T, 1), device=x.device, dtype=torch.float32)
+        if out.numel() == 0:
+            return out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(ctx.lib.w2l_disc_forward(ctx.h, self._p(x), self._p(out), B, T, C.c_void_p(stream)))
         return out
