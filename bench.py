@@ -194,6 +194,17 @@ def measure_extra(dev):
                                    "uint8 predictions back (inference.py:134-140,259-265,269 fused)", "ms": dt * 1e3,
                          "crops_per_s": n / dt, "h2d_bytes": int(faces.numel() + melh.numel() * 4), "d2h_bytes": int(outh.numel())}
         del g
+        # the fp32-faithful precision mode (split fp16 operands, 3 MMAs per product) on the headline workload
+        gx = Wav2Lip()
+        gx.precision = _lib.PREC_F32X
+        gx = gx.to(dev).eval()
+        melx = (torch.rand((B_DEFAULT, T_DEFAULT, 1, 80, 16)) * 8 - 4).to(dev)
+        facex = torch.rand((B_DEFAULT, 6, T_DEFAULT, 96, 96)).to(dev)
+        ms = timeit(lambda: gx(melx, facex), 5)
+        out["generator_f32x"] = {"config": "Wav2Lip.forward B=128,T=5 in W2L_PREC_F32X (hi+lo fp16 operands, ~22-bit significands; "
+                                           "max-abs error 1.3e-4 on the stress weights vs 3.7e-3 in the default mode)",
+                                 "ms": ms, "crops_per_s": B_DEFAULT * T_DEFAULT / ms * 1e3}
+        del gx, melx, facex
         for nfr, key in ((10000, "mel_10k"), (1000000, "mel_1M")):
             wav = (0.1 * torch.randn((nfr - 1) * 200, device=dev)).float()
             ms = timeit(lambda: audio.melspectrogram(wav), 10)

@@ -52,6 +52,9 @@ extern "C" {
 /* operand precision of the tensor-core path (accumulation is always fp32) */
 #define W2L_PREC_F16  0   /* fp16 operands: 10-bit mantissa, same as TF32 (default) */
 #define W2L_PREC_BF16 1   /* bf16 operands: for checkpoints whose activations exceed the fp16 range */
+#define W2L_PREC_F32X 2   /* fp32-faithful: every activation and weight is carried as hi + lo (two fp16 values, ~22
+                             significant bits) and each product as x_hi*w_hi + x_lo*w_hi + x_hi*w_lo on the tensor
+                             cores (3 MMAs, generic kernel only): ~1e-6 relative per block, ~1/4 of the throughput */
 
 typedef struct w2l_ctx w2l_ctx;
 

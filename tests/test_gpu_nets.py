@@ -230,6 +230,46 @@ def test_disc_vs_reference_golden(golden_dir):
     assert torch.allclose(p_b1.flatten(), p.flatten()[1::2], atol=0, rtol=0)
 
 
+def test_fp32_faithful_mode_meets_1e3_on_stress_weights(golden_dir):
+    """W2L_PREC_F32X: split fp16 operands (hi + lo, 3 MMAs per product): the stress weights that the fast mode
+    can only hold to 8e-3 (TF32-class arithmetic, see tests/test_precision_model.py) meet north_star's 1e-3 bar."""
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip, Wav2Lip_disc_qual
+    gold = np.load(os.path.join(golden_dir, "generator.npz"))
+    g = Wav2Lip()
+    g.precision = _lib.PREC_F32X
+    g.load_state_dict(O.make_state_dict("generator", 0), strict=True)
+    g = g.cuda().eval()
+    mel, face = O.make_generator_inputs(2, 0)
+    with torch.no_grad():
+        y = g(mel.cuda(), face.cuda()).cpu().numpy()
+    err = np.abs(y - gold["gen4_out"]).max()
+    assert err <= BAR, err
+    assert err <= 3e-4, err          # measured ~1e-4 (30x below the fast mode on these weights)
+    mel5, face5 = O.make_generator_inputs(2, seed=1, t=5)
+    with torch.no_grad():
+        y5 = g(mel5.cuda(), face5.cuda()).cpu().numpy()
+    assert np.abs(y5 - gold["gen5_out"]).max() <= 3e-4
+    gs = np.load(os.path.join(golden_dir, "syncnet.npz"))
+    s = SyncNet_color()
+    s.precision = _lib.PREC_F32X
+    s.load_state_dict(O.make_state_dict("syncnet", 0), strict=True)
+    s = s.cuda().eval()
+    mel, face = O.make_syncnet_inputs(3, 0)
+    with torch.no_grad():
+        a, v = s(mel.cuda(), face.cuda())
+    assert np.abs(a.cpu().numpy() - gs["sync_a"]).max() <= 2e-5
+    assert np.abs(v.cpu().numpy() - gs["sync_v"]).max() <= 2e-5
+    gd = np.load(os.path.join(golden_dir, "disc.npz"))
+    d = Wav2Lip_disc_qual()
+    d.precision = _lib.PREC_F32X
+    d.load_state_dict(O.make_state_dict("disc", 0), strict=True)
+    d = d.cuda().eval()
+    with torch.no_grad():
+        p = d(O.make_disc_inputs(2, 5, 0).cuda())
+    assert np.abs(p.cpu().numpy() - gd["disc_out"]).max() <= 2e-5
+
+
 def test_bf16_precision_mode_runs(golden_dir):
     """The bf16-operand build of the same kernels (for checkpoints outside the fp16 range)."""
     from wav2lip_b200 import _lib

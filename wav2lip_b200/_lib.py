@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 W2L_OK, W2L_EINVAL, W2L_ENODEV, W2L_ECUDA, W2L_ENOMEM, W2L_ESTATE = 0, -1, -2, -3, -4, -5
 NET_GENERATOR, NET_SYNCNET, NET_DISC = 0, 1, 2
 BLOCK_CONV_BN_RELU, BLOCK_CONVT_BN_RELU, BLOCK_CONV_LRELU, BLOCK_CONV_PLAIN = 0, 1, 2, 3
-PREC_F16, PREC_BF16 = 0, 1
+PREC_F16, PREC_BF16, PREC_F32X = 0, 1, 2
 
 # every symbol include/w2l.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [

@@ -41,6 +41,8 @@ struct IngestParams {
     int Wp, x_off;      // destination row pitch (pixels) and left border
     long long sB, sC, sT;  // source strides in elements for b, c, t
     int y_off, Wsrc;       // source row offset / row pitch
+    int lo_off;            // > 0: split-operand mode, also write lo = x - fp16(x) at channel + lo_off
+    int Cpix;              // channels per pixel of the destination (= Cpad, or 2*Cpad with a lo plane)
 };
 
 template <bool kBF16>
@@ -53,7 +55,7 @@ __global__ void ingest_kernel(const IngestParams p) {
         const int n = (int)(i / ((long long)p.W * p.H));
         const int b = n % p.B, t = n / p.B;
         const float* s = p.src + b * p.sB + t * p.sT + (long long)(y + p.y_off) * p.Wsrc + x;
-        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpad;
+        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpix;
         for (int c0 = 0; c0 < p.Cpad; c0 += 8) {
             uint16_t h[8];
 #pragma unroll
@@ -67,6 +69,20 @@ __global__ void ingest_kernel(const IngestParams p) {
             o.z = h[4] | ((uint32_t)h[5] << 16);
             o.w = h[6] | ((uint32_t)h[7] << 16);
             *reinterpret_cast<uint4*>(d + c0) = o;
+            if (p.lo_off > 0) {
+                uint16_t l[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int c = c0 + j;
+                    l[j] = (c < p.C) ? to16<kBF16>(__ldg(s + c * p.sC) - from16<kBF16>(h[j])) : (uint16_t)0;
+                }
+                uint4 q;
+                q.x = l[0] | ((uint32_t)l[1] << 16);
+                q.y = l[2] | ((uint32_t)l[3] << 16);
+                q.z = l[4] | ((uint32_t)l[5] << 16);
+                q.w = l[6] | ((uint32_t)l[7] << 16);
+                *reinterpret_cast<uint4*>(d + p.lo_off + c0) = q;
+            }
         }
     }
 }
@@ -78,6 +94,8 @@ struct IngestU8Params {
     const unsigned char* src;  // (N, H, W, 3)
     uint16_t* dst;
     int N, H, W, Cpad, Wp, x_off;
+    int lo_off;  // > 0: split-operand mode, also write the lo plane
+    int Cpix;    // channels per pixel of the destination
 };
 
 template <bool kBF16>
@@ -89,15 +107,18 @@ __global__ void ingest_u8_kernel(const IngestU8Params p) {
         const int y = (int)((i / p.W) % p.H);
         const int n = (int)(i / ((long long)p.W * p.H));
         const unsigned char* s = p.src + i * 3;
-        uint16_t h[8];
+        uint16_t h[8], l[8];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
             const float v = (float)((double)s[c] / 255.0);
             h[3 + c] = to16<kBF16>(v);
+            l[3 + c] = to16<kBF16>(v - from16<kBF16>(h[3 + c]));
             h[c] = (y >= p.H / 2) ? (uint16_t)0 : h[3 + c];
+            l[c] = (y >= p.H / 2) ? (uint16_t)0 : l[3 + c];
         }
         h[6] = h[7] = 0;
-        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpad;
+        l[6] = l[7] = 0;
+        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpix;
         uint4 o;
         o.x = h[0] | ((uint32_t)h[1] << 16);
         o.y = h[2] | ((uint32_t)h[3] << 16);
@@ -105,6 +126,15 @@ __global__ void ingest_u8_kernel(const IngestU8Params p) {
         o.w = 0u;
         *reinterpret_cast<uint4*>(d) = o;
         for (int c0 = 8; c0 < p.Cpad; c0 += 8) *reinterpret_cast<uint4*>(d + c0) = make_uint4(0u, 0u, 0u, 0u);
+        if (p.lo_off > 0) {
+            uint4 q;
+            q.x = l[0] | ((uint32_t)l[1] << 16);
+            q.y = l[2] | ((uint32_t)l[3] << 16);
+            q.z = l[4] | ((uint32_t)l[5] << 16);
+            q.w = 0u;
+            *reinterpret_cast<uint4*>(d + p.lo_off) = q;
+            for (int c0 = 8; c0 < p.Cpad; c0 += 8) *reinterpret_cast<uint4*>(d + p.lo_off + c0) = make_uint4(0u, 0u, 0u, 0u);
+        }
     }
 }
 
@@ -125,7 +155,7 @@ __global__ void mel_chunk_kernel(const float* mel, long long F, double mult, int
 
 // NHWC 16-bit (channel slice of a buffer with channel pitch Cs) -> NCHW fp32
 template <bool kBF16>
-__global__ void export_kernel(const uint16_t* src, float* dst, int N, int H, int W, int C, int Cs, int f32src) {
+__global__ void export_kernel(const uint16_t* src, float* dst, int N, int H, int W, int C, int Cs, int f32src, int lo_off) {
     const long long total = (long long)N * C * H * W;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
          i += (long long)gridDim.x * blockDim.x) {
@@ -134,7 +164,8 @@ __global__ void export_kernel(const uint16_t* src, float* dst, int N, int H, int
         const int c = (int)((i / ((long long)W * H)) % C);
         const int n = (int)(i / ((long long)W * H * C));
         const long long so = (((long long)n * H + y) * W + x) * Cs + c;
-        dst[i] = f32src ? reinterpret_cast<const float*>(src)[so] : from16<kBF16>(src[so]);
+        dst[i] = f32src ? reinterpret_cast<const float*>(src)[so]
+                        : from16<kBF16>(src[so]) + (lo_off > 0 ? from16<kBF16>(src[so + lo_off]) : 0.0f);
     }
 }
 
@@ -144,6 +175,7 @@ struct PackParams {
     int ntaps, cout, cin, cout_pad, cin_pad;
     long long s_co, s_ci, s_r, s_s;  // source strides (elements)
     signed char r[49], s[49];        // filter coordinates of each packed tap
+    int lo;                          // 1: pack w - fp16(w) (the lo plane of the split-operand mode)
 };
 
 template <bool kBF16>
@@ -156,6 +188,7 @@ __global__ void pack_w_kernel(const PackParams p) {
         const int t = (int)(i / ((long long)p.cin_pad * p.cout_pad));
         float v = 0.0f;
         if (ci < p.cin && co < p.cout) v = p.src[co * p.s_co + ci * p.s_ci + p.r[t] * p.s_r + p.s[t] * p.s_s];
+        if (p.lo) v -= from16<kBF16>(to16<kBF16>(v));
         p.dst[i] = to16<kBF16>(v);
     }
 }
@@ -221,12 +254,17 @@ __global__ void l2norm_kernel(const float* x, float* y, int B, int D) {
 
 // one warp per row: prob = sigmoid(dot(x[row,:D], w) + b), x is 16-bit
 template <bool kBF16>
-__global__ void disc_head_kernel(const uint16_t* x, const float* w, const float* b, float* prob, int rows, int D) {
+__global__ void disc_head_kernel(const uint16_t* x, const float* w, const float* b, float* prob, int rows, int D, int pitch,
+                                 int lo_off) {
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
     float s = 0.0f;
-    for (int i = lane; i < D; i += 32) s = fmaf(from16<kBF16>(x[(long long)row * D + i]), w[i], s);
+    for (int i = lane; i < D; i += 32) {
+        float xv = from16<kBF16>(x[(long long)row * pitch + i]);
+        if (lo_off > 0) xv += from16<kBF16>(x[(long long)row * pitch + lo_off + i]);
+        s = fmaf(xv, w[i], s);
+    }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) prob[row] = 1.0f / (1.0f + __expf(-(s + b[0])));

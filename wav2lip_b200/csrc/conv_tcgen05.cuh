@@ -42,7 +42,8 @@
 namespace w2l {
 
 constexpr int kTileM = 128;
-constexpr int kMaxTaps = 49;
+constexpr int kMaxTaps = 49;              // filter taps of one launch
+constexpr int kMaxSteps = 3 * kMaxTaps;   // K-loop entries: x3 in the split-operand (fp32-faithful) precision mode
 constexpr int kConvThreads = 256;
 constexpr int kSmemBudget = 224 * 1024;  // patch kernels: weights + patch ring + staging; barriers live in the extra KB
 constexpr int kSmemExtra = 2048;         // 1024 alignment slack + barriers
@@ -64,6 +65,9 @@ struct EpiParams {
     // fused generator head (kHead kernels only): out = sigmoid(W[3x32] relu(y) + b), fp32 NCHW/5-D
     const float* head_w;
     const float* head_b;
+    // split-operand (fp32-faithful) mode: every value is stored as hi + lo (two fp16 planes, lo_off channels apart)
+    int x2;
+    int out_lo_off, res_lo_off;
     float* head_out;
     unsigned char* head_out_u8;  // if set: (N,H,W,3) uint8 = trunc(sigmoid * 255.f), inference.py:265,269
     int head_B, head_T;     // n = t*head_B + b ; T=1,B=N for the 4-D call
@@ -84,8 +88,13 @@ struct alignas(64) ConvParams {
     int ntaps, kc_per_tap;
     unsigned stage_tx_bytes;  // bytes both TMA loads of one stage deliver
     EpiParams ep;
-    signed char dx[kMaxTaps];
-    signed char dy[kMaxTaps];
+    // K-loop entries ("steps"): one per filter tap, or three per tap in the split-operand mode
+    // (x_hi*w_hi, x_lo*w_hi, x_hi*w_lo).  a_lo selects the lo plane of the activations, b_slab the weight slab.
+    int a_lo_off;                    // channel offset of the lo plane inside a pixel (0 in the 16-bit modes)
+    signed char dx[kMaxSteps];
+    signed char dy[kMaxSteps];
+    unsigned char a_lo[kMaxSteps];
+    unsigned char b_slab[kMaxSteps];
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -266,6 +275,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr
                     f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
                     f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
                 }
+                if (e.x2) {  // lo plane of the residual
+#pragma unroll
+                    for (int j = 0; j < CH / 8; ++j) {
+                        const uint4 r = __ldg(rp + (e.res_lo_off >> 3) + j);
+                        const float2 a = unpack2<kBF16>(r.x), b = unpack2<kBF16>(r.y);
+                        const float2 c = unpack2<kBF16>(r.z), d = unpack2<kBF16>(r.w);
+                        f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                        f[8 * j + 4] += c.x; f[8 * j + 5] += c.y; f[8 * j + 6] += d.x; f[8 * j + 7] += d.y;
+                    }
+                }
             }
             if (e.act == ACT_RELU) {
 #pragma unroll
@@ -303,6 +322,16 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr
                     o.z = pack2<kBF16>(f[8 * j + 4], f[8 * j + 5]);
                     o.w = pack2<kBF16>(f[8 * j + 6], f[8 * j + 7]);
                     op[j] = o;
+                    if (e.x2) {  // lo = fp16(v - fp16(v)): together the two planes carry ~22 significant bits
+                        const float2 h0 = unpack2<kBF16>(o.x), h1 = unpack2<kBF16>(o.y);
+                        const float2 h2 = unpack2<kBF16>(o.z), h3 = unpack2<kBF16>(o.w);
+                        uint4 l;
+                        l.x = pack2<kBF16>(f[8 * j + 0] - h0.x, f[8 * j + 1] - h0.y);
+                        l.y = pack2<kBF16>(f[8 * j + 2] - h1.x, f[8 * j + 3] - h1.y);
+                        l.z = pack2<kBF16>(f[8 * j + 4] - h2.x, f[8 * j + 5] - h2.y);
+                        l.w = pack2<kBF16>(f[8 * j + 6] - h3.x, f[8 * j + 7] - h3.y);
+                        op[(e.out_lo_off >> 3) + j] = l;
+                    }
                 }
             }
         }
@@ -391,9 +420,9 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
                         mbar_arrive_expect_tx(full_bar(stage), p.stage_tx_bytes);
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt)
-                            tma_load_4d(a_dst + mt * Cfg::kATile, &p.tmA, full_bar(stage), kc * BK, x_in0[mt] + p.dx[t],
-                                        y_in0[mt] + p.dy[t], n0[mt]);
-                        tma_load_3d(b_dst, &p.tmB, full_bar(stage), kc * BK, nt * BN, t);
+                            tma_load_4d(a_dst + mt * Cfg::kATile, &p.tmA, full_bar(stage), kc * BK + (p.a_lo[t] ? p.a_lo_off : 0),
+                                        x_in0[mt] + p.dx[t], y_in0[mt] + p.dy[t], n0[mt]);
+                        tma_load_3d(b_dst, &p.tmB, full_bar(stage), kc * BK, nt * BN, p.b_slab[t]);
                         if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
                 }

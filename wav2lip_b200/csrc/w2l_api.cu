@@ -98,6 +98,7 @@ struct Act {
     bool f32 = false;
     int Wp = 0;     // row pitch in pixels (0 = W); > W only for the zero-bordered first-layer inputs
     int x_off = 0;  // left border of those inputs
+    int lo_off = 0;   // split-operand mode: channel distance from the hi plane to the lo plane of the same pixel
     int wstride = 1;  // folded views: pixels between consecutive windows (= the conv's horizontal stride)
     int nwin = 0;     // folded views: number of windows per row (= output width); 0 = W
     int pitch() const { return Wp ? Wp : W; }
@@ -108,6 +109,7 @@ struct Act {
 struct PackedW {
     uint16_t* w = nullptr;  // [ntaps][cout_pad][cin_pad]
     int ntaps = 0, cout_pad = 0, cin_pad = 0;
+    int nslabs = 0;                   // weight slabs stored: ntaps, or 2*ntaps (hi then lo) in the split-operand mode
     std::vector<signed char> dx, dy;  // input offset of each tap relative to (out * stride)
     int py = 0, px = 0;               // output phase (transposed conv)
     // "kw folded into K" form for tiny-Cin first layers: one K row = kw taps x Cp channels (zero padded to kfold)
@@ -155,6 +157,7 @@ struct Op {
     const void* aux_in = nullptr;
     int aux_rows = 0, aux_dim = 0;
     int aux_out = 0;  // which caller output
+    int aux_pitch = 0, aux_lo = 0;
 };
 
 struct Plan {
@@ -164,11 +167,13 @@ struct Plan {
     size_t bytes = 0;
     std::map<int, Act> layer_out;  // layer index -> activation view (debug export)
     long long last_used = 0;       // LRU stamp
+    bool x2 = false;               // split-operand precision: activations carry hi and lo planes
 };
 
 struct w2l_ctx {
     int device = 0;
     bool bf16 = false;
+    bool x2 = false;        // W2L_PREC_F32X: split fp16 operands (hi + lo), generic kernel only
     int num_sms = 148;
     bool keep_all = false;  // debug: no buffer reuse, every layer output stays readable
     bool use_patch = true;   // W2L_DISABLE_HALO=1 turns the patch kernel off (A/B testing)
@@ -213,10 +218,12 @@ static int plan_alloc(Plan* pl, void** p, size_t bytes) {
 
 static int plan_act(Plan* pl, Act* a, int N, int H, int W, int C, bool f32 = false) {
     void* p = nullptr;
-    const size_t bytes = (size_t)N * H * W * C * (f32 ? 4 : 2);
+    const bool planes = pl->x2 && !f32;
+    const size_t bytes = (size_t)N * H * W * C * (f32 ? 4 : 2) * (planes ? 2 : 1);
     CKR(plan_alloc(pl, &p, bytes));
     a->base = (uint16_t*)p;
-    a->N = N; a->H = H; a->W = W; a->Cs = C; a->c_off = 0; a->C = C; a->f32 = f32;
+    a->N = N; a->H = H; a->W = W; a->Cs = planes ? 2 * C : C; a->c_off = 0; a->C = C; a->f32 = f32;
+    a->lo_off = planes ? C : 0;
     return W2L_OK;
 }
 
@@ -406,6 +413,9 @@ static void fill_epi(EpiParams* e, const ConvArgs& a) {
     e->scale = a.scale + a.ch_off;
     e->shift = a.shift + a.ch_off;
     e->head_w = a.head_w; e->head_b = a.head_b; e->head_out = nullptr; e->head_B = a.head_B; e->head_T = a.head_T;
+    e->x2 = (a.out.lo_off > 0 || (a.res && a.res->lo_off > 0)) ? 1 : 0;
+    e->out_lo_off = a.out.lo_off;
+    e->res_lo_off = a.res ? a.res->lo_off : 0;
 }
 
 static int encode_act_map(w2l_ctx* ctx, CUtensorMap* tm, const Act& in, int BK, int bx, int by, int bn, int sx, int sy,
@@ -413,7 +423,7 @@ static int encode_act_map(w2l_ctx* ctx, CUtensorMap* tm, const Act& in, int BK, 
     EncodeTiledFn enc = get_encode_fn();
     const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    cuuint64_t dims[4] = {(cuuint64_t)in.C, (cuuint64_t)(in.nwin ? in.nwin : in.W), (cuuint64_t)in.H, (cuuint64_t)in.N};
+    cuuint64_t dims[4] = {(cuuint64_t)(in.lo_off + in.C), (cuuint64_t)(in.nwin ? in.nwin : in.W), (cuuint64_t)in.H, (cuuint64_t)in.N};
     cuuint64_t strides[3] = {(cuuint64_t)in.Cs * in.wstride * 2, (cuuint64_t)in.pitch() * in.Cs * 2, (cuuint64_t)in.H * in.pitch() * in.Cs * 2};
     cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)bx, (cuuint32_t)by, (cuuint32_t)bn};
     cuuint32_t es[4] = {1, (cuuint32_t)sx, (cuuint32_t)sy, 1};
@@ -429,7 +439,7 @@ static int encode_w_map(w2l_ctx* ctx, CUtensorMap* tm, const PackedW& w, int BK,
     EncodeTiledFn enc = get_encode_fn();
     const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const CUtensorMapSwizzle sw = BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : BK == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)w.ntaps};
+    cuuint64_t dims[3] = {(cuuint64_t)w.cin_pad, (cuuint64_t)w.cout_pad, (cuuint64_t)(w.nslabs ? w.nslabs : w.ntaps)};
     cuuint64_t strides[2] = {(cuuint64_t)w.cin_pad * 2, (cuuint64_t)w.cin_pad * w.cout_pad * 2};
     cuuint32_t box[3] = {(cuuint32_t)BK, (cuuint32_t)BN, 1};
     cuuint32_t es[3] = {1, 1, 1};
@@ -583,7 +593,7 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     fill_epi(&p.ep, a);
     // staged epilogue (TMA residual load + TMA store) for 16-bit outputs; the head / fp32 outputs keep direct stores
     p.tma_epi = 0;
-    if (ctx->use_tma_epi && !a.head && !a.out.f32) {
+    if (ctx->use_tma_epi && !ctx->x2 && !a.head && !a.out.f32) {
         EncodeTiledFn enc = get_encode_fn();
         const int EW = BN < 64 ? BN : 64;
         const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
@@ -607,7 +617,21 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
         p.epi_box_bytes = (unsigned)(bw * bh * bn * EW * 2);
     }
     if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
-    for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; }
+    if (ctx->x2) {
+        // split operands: x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (the dropped x_lo*w_lo term is ~2^-22 relative)
+        if (a.in.lo_off <= 0 || w.nslabs != 2 * w.ntaps) return fail(W2L_ESTATE, "%s: split-operand mode needs hi/lo planes", a.name.c_str());
+        int k = 0;
+        for (int t = 0; t < w.ntaps; ++t)
+            for (int v = 0; v < 3; ++v, ++k) {
+                p.dx[k] = w.dx[t]; p.dy[k] = w.dy[t];
+                p.a_lo[k] = (v == 1) ? 1 : 0;
+                p.b_slab[k] = (unsigned char)((v == 2) ? w.ntaps + t : t);
+            }
+        p.ntaps = 3 * w.ntaps;
+        p.a_lo_off = a.in.lo_off;
+    } else {
+        for (int t = 0; t < w.ntaps; ++t) { p.dx[t] = w.dx[t]; p.dy[t] = w.dy[t]; p.a_lo[t] = 0; p.b_slab[t] = (unsigned char)t; }
+    }
     const int total = ((m_tiles + op.MT - 1) / op.MT) * p.n_tiles;
     op.grid = std::min(total, ctx->num_sms);
     op.flops = 2.0 * a.macs_per_pixel * (double)a.Wl * a.Hl * a.in.N;
@@ -765,19 +789,25 @@ static int pack_taps(w2l_ctx* ctx, PackedW* pw, const float* src, int cout, int 
     pp.s_r = kw; pp.s_s = 1;
     for (size_t t = 0; t < rs.size(); ++t) { pp.r[t] = (signed char)rs[t].first; pp.s[t] = (signed char)rs[t].second; }
     const size_t n = (size_t)pp.ntaps * pp.cout_pad * pp.cin_pad;
+    const int planes = (ctx->x2 && !dst_override) ? 2 : 1;
     if (dst_override) pp.dst = dst_override;
     else {
         void* d = nullptr;
-        CKR(dev_alloc(&d, n * 2));
-        ctx->weight_bytes += n * 2;
+        CKR(dev_alloc(&d, n * 2 * planes));
+        ctx->weight_bytes += n * 2 * planes;
         pp.dst = (uint16_t*)d;
         pw->w = pp.dst;
         pw->ntaps = pp.ntaps; pw->cout_pad = pp.cout_pad; pw->cin_pad = pp.cin_pad;
+        pw->nslabs = pp.ntaps * planes;
     }
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
-    if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
-    else pack_w_kernel<false><<<blocks, 256, 0, st>>>(pp);
-    ctx->launches++;
+    for (int pl_ = 0; pl_ < planes; ++pl_) {  // hi slabs, then (split-operand mode) the lo slabs w - fp16(w)
+        pp.lo = pl_;
+        if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
+        else pack_w_kernel<false><<<blocks, 256, 0, st>>>(pp);
+        ctx->launches++;
+        pp.dst += n;
+    }
     CK(cudaGetLastError());
     return W2L_OK;
 }
@@ -830,7 +860,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
             for (int s = 0; s < L.kw; ++s) { rs.push_back({r, s}); pw.dy.push_back((signed char)(r - L.ph)); pw.dx.push_back((signed char)(s - L.pw)); }
         CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, false, rs, pad_to, st));
         lw->ph.push_back(pw);
-    } else if (in_hw1 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) {
+    } else if (in_hw1 && !ctx->x2 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) {
         // out[n, y, x, co] = sum_ci in[n, ci] * W[ci, co, y, x]  -> GEMM with columns (y, x, co)
         lw->gemm_convT = true;
         reps = L.kh * L.kw;
@@ -870,7 +900,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
                 CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st));
                 lw->ph.push_back(pw);
             }
-        if (L.cout == kCtBN && L.kh == 3 && L.kw == 3 && L.sh == 2 && L.sw == 2 && L.ph == 1 && L.pw == 1 && L.out_pad == 1) {
+        if (!ctx->x2 && L.cout == kCtBN && L.kh == 3 && L.kw == 3 && L.sh == 2 && L.sw == 2 && L.ph == 1 && L.pw == 1 && L.out_pad == 1) {
             // all nine taps in (r, s) order for the fused four-phase kernel
             std::vector<std::pair<int, int>> rs;
             PackedW pw;
@@ -928,13 +958,13 @@ struct TmpPool {  // two ping-pong temporaries per chain, grown on demand
 static int tmp_act(w2l_ctx* ctx, Plan* pl, TmpPool* tp, Act* a, int N, int H, int W, int C, const uint16_t* avoid) {
     int s = tp->next;
     if (tp->slot[s].base != nullptr && tp->slot[s].base == avoid) s ^= 1;
-    const size_t need_b = (size_t)N * H * W * C * 2;
+    const size_t need_b = (size_t)N * H * W * C * 2 * (pl->x2 ? 2 : 1);
     if (ctx->keep_all || tp->cap[s] < need_b) {
         CKR(plan_act(pl, &tp->slot[s], N, H, W, C));
         tp->cap[s] = need_b;
     }
     Act v = tp->slot[s];
-    v.N = N; v.H = H; v.W = W; v.Cs = C; v.c_off = 0; v.C = C;
+    v.N = N; v.H = H; v.W = W; v.Cs = pl->x2 ? 2 * C : C; v.c_off = 0; v.C = C; v.lo_off = pl->x2 ? C : 0;
     *a = v;
     tp->next = s ^ 1;
     return W2L_OK;
@@ -948,8 +978,11 @@ static void add_ingest(Plan* pl, const char* name, int src_id, const Act& dst, i
     op.ingest_src = src_id;
     IngestParams& ip = op.ip;
     ip.src = nullptr; ip.dst = dst.base;
-    ip.N = dst.N; ip.B = B; ip.C = C; ip.H = dst.H; ip.W = dst.W; ip.Cpad = dst.Cs;
+    ip.N = dst.N; ip.B = B; ip.C = C; ip.H = dst.H; ip.W = dst.W;
+    ip.Cpad = dst.lo_off > 0 ? dst.lo_off : dst.Cs;  // logical (padded) channels; Cs is the pixel pitch
+    ip.Cpix = dst.Cs;
     ip.Wp = dst.pitch(); ip.x_off = dst.x_off;
+    ip.lo_off = dst.lo_off;
     ip.sB = sB; ip.sC = sC; ip.sT = sT; ip.y_off = y_off; ip.Wsrc = Wsrc;
     pl->ops.push_back(op);
 }
@@ -1089,6 +1122,7 @@ static int build_disc_plan(w2l_ctx* ctx, Plan* pl) {
     op.type = OP_DISC_HEAD;
     op.name = "binary_pred";
     op.aux_in = feat.base; op.aux_rows = N; op.aux_dim = 512; op.aux_out = 0;
+    op.aux_pitch = feat.Cs; op.aux_lo = feat.lo_off;
     pl->ops.push_back(op);
     return W2L_OK;
 }
@@ -1116,6 +1150,7 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
     }
     std::unique_ptr<Plan> pl(new Plan());
     pl->net = net; pl->B = B; pl->T = T;
+    pl->x2 = ctx->x2;
     pl->N = (net == W2L_NET_SYNCNET) ? B : (T > 0 ? B * T : B);
     int r = W2L_OK;
     if (net == W2L_NET_GENERATOR) r = build_generator_plan(ctx, pl.get());
@@ -1136,7 +1171,7 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                 if (u8 && op.ingest_src == 1) {  // uint8 crops: mask + concat + /255 fused into the ingest
                     IngestU8Params up;
                     up.src = (const unsigned char*)in1; up.dst = op.ip.dst;
-                    up.N = op.ip.N; up.H = op.ip.H; up.W = op.ip.W; up.Cpad = op.ip.Cpad; up.Wp = op.ip.Wp; up.x_off = op.ip.x_off;
+                    up.N = op.ip.N; up.H = op.ip.H; up.W = op.ip.W; up.Cpad = op.ip.Cpad; up.Wp = op.ip.Wp; up.x_off = op.ip.x_off; up.lo_off = op.ip.lo_off; up.Cpix = op.ip.Cpix;
                     const long long tot = (long long)up.N * up.H * up.W;
                     const int blk = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
                     if (ctx->bf16) ingest_u8_kernel<true><<<blk, 256, 0, st>>>(up);
@@ -1169,8 +1204,8 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
             }
             case OP_DISC_HEAD: {
                 const NetW& nw = ctx->nets[W2L_NET_DISC];
-                if (ctx->bf16) disc_head_kernel<true><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim);
-                else disc_head_kernel<false><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim);
+                if (ctx->bf16) disc_head_kernel<true><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim, op.aux_pitch, op.aux_lo);
+                else disc_head_kernel<false><<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const uint16_t*)op.aux_in, nw.head_w, nw.head_b, (float*)out0, op.aux_rows, op.aux_dim, op.aux_pitch, op.aux_lo);
                 ctx->launches++;
                 break;
             }
@@ -1310,7 +1345,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { cudaGetLastError(); return fail(W2L_ENODEV, "no CUDA device (this library has no CPU path)"); }
     if (device < 0 || device >= ndev) return fail(W2L_EINVAL, "device %d out of range (%d devices)", device, ndev);
-    if (precision != W2L_PREC_F16 && precision != W2L_PREC_BF16) return fail(W2L_EINVAL, "unknown precision %d", precision);
+    if (precision != W2L_PREC_F16 && precision != W2L_PREC_BF16 && precision != W2L_PREC_F32X) return fail(W2L_EINVAL, "unknown precision %d", precision);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(W2L_ENODEV, "device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major, prop.minor);
@@ -1319,6 +1354,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     w2l_ctx* ctx = new w2l_ctx();
     ctx->device = device;
     ctx->bf16 = precision == W2L_PREC_BF16;
+    ctx->x2 = precision == W2L_PREC_F32X;
     ctx->num_sms = prop.multiProcessorCount;
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
@@ -1346,6 +1382,9 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_mt2 = !(e5 && e5[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
         ctx->use_ctfused = !(e4 && e4[0] == '1');
+        if (ctx->x2) {  // the split-operand mode runs on the generic kernel with the direct epilogue only
+            ctx->use_patch = ctx->use_fold = ctx->use_fold_s2 = ctx->use_ctfused = ctx->use_tma_epi = false;
+        }
         if (ctx->use_fold) {
             // the folded first layers need a tensor map whose pixel stride (16 B) is smaller than its inner extent
             // (128 B): probe once that the driver encodes such overlapping windows
@@ -1575,6 +1614,7 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     int r = load_layer(ctx, &scratch.layers[0], L, weight, bias, bn_w, bn_b, bn_m, bn_v, H == 1 && W == 1, true, st);
     Plan pl;
     pl.net = W2L_NET_DISC; pl.N = N; pl.B = N; pl.T = 0;
+    pl.x2 = ctx->x2;
     Act in, out;
     if (r == W2L_OK) r = plan_input_act(&pl, &in, N, H, W, L.cin, scratch.layers[0], L);
     if (r == W2L_OK) r = plan_act(&pl, &out, N, Ho, Wo, L.cout);
@@ -1590,8 +1630,8 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     if (r == W2L_OK) {
         const long long total = (long long)N * L.cout * Ho * Wo;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-        if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, L.cout, 0);
-        else export_kernel<false><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, L.cout, 0);
+        if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, out.Cs, 0, out.lo_off);
+        else export_kernel<false><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, out.Cs, 0, out.lo_off);
         ctx->launches++;
         cudaError_t e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) r = fail(W2L_ECUDA, "conv block failed: %s", cudaGetErrorString(e));
@@ -1619,8 +1659,8 @@ int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y, int* n, i
     const long long total = (long long)a.N * a.C * a.H * a.W;
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     const uint16_t* src = a.f32 ? (const uint16_t*)((const float*)a.base + a.c_off) : a.ptr();
-    if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0);
-    else export_kernel<false><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0);
+    if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0, a.f32 ? 0 : a.lo_off);
+    else export_kernel<false><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0, a.f32 ? 0 : a.lo_off);
     ctx->launches++;
     CK(cudaGetLastError());
     return W2L_OK;
