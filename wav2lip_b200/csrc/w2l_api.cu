@@ -1173,7 +1173,7 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                     up.src = (const unsigned char*)in1; up.dst = op.ip.dst;
                     up.N = op.ip.N; up.H = op.ip.H; up.W = op.ip.W; up.Cpad = op.ip.Cpad; up.Wp = op.ip.Wp; up.x_off = op.ip.x_off; up.lo_off = op.ip.lo_off; up.Cpix = op.ip.Cpix;
                     const long long tot = (long long)up.N * up.H * up.W;
-                    const int blk = (int)std::min<long long>((tot + 255) / 256, 148 * 16);
+                    const int blk = (int)std::min<long long>((tot + 255) / 256, ctx->num_sms * 16);
                     if (ctx->bf16) ingest_u8_kernel<true><<<blk, 256, 0, st>>>(up);
                     else ingest_u8_kernel<false><<<blk, 256, 0, st>>>(up);
                     ctx->launches++;
@@ -1182,7 +1182,7 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                 IngestParams ip = op.ip;
                 ip.src = (const float*)(op.ingest_src == 0 ? in0 : in1);
                 const long long total = (long long)ip.N * ip.H * ip.W;
-                const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+                const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
                 if (ctx->bf16) ingest_kernel<true><<<blocks, 256, 0, st>>>(ip);
                 else ingest_kernel<false><<<blocks, 256, 0, st>>>(ip);
                 ctx->launches++;
@@ -1629,7 +1629,7 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
     }
     if (r == W2L_OK) {
         const long long total = (long long)N * L.cout * Ho * Wo;
-        const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
         if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, out.Cs, 0, out.lo_off);
         else export_kernel<false><<<blocks, 256, 0, st>>>(out.base, y, N, Ho, Wo, L.cout, out.Cs, 0, out.lo_off);
         ctx->launches++;
@@ -1657,7 +1657,7 @@ int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y, int* n, i
     DeviceGuard g(ctx->device);
     cudaStream_t st = (cudaStream_t)stream;
     const long long total = (long long)a.N * a.C * a.H * a.W;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
     const uint16_t* src = a.f32 ? (const uint16_t*)((const float*)a.base + a.c_off) : a.ptr();
     if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0, a.f32 ? 0 : a.lo_off);
     else export_kernel<false><<<blocks, 256, 0, st>>>(src, y, a.N, a.H, a.W, a.C, a.Cs, a.f32 ? 1 : 0, a.f32 ? 0 : a.lo_off);
@@ -1710,7 +1710,7 @@ int w2l_mel_chunks(w2l_ctx* ctx, const float* mel, int64_t n_frames, double fps,
     if (n_chunks != w2l_mel_num_chunks(n_frames, fps)) return fail(W2L_EINVAL, "n_chunks %lld does not match w2l_mel_num_chunks = %lld", (long long)n_chunks, (long long)w2l_mel_num_chunks(n_frames, fps));
     DeviceGuard g(ctx->device);
     const long long total = (long long)n_chunks * 1280;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
     mel_chunk_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, n_frames, 80.0 / fps, (int)n_chunks, chunks);
     ctx->launches++;
     CK(cudaGetLastError());
