@@ -158,6 +158,8 @@ struct Op {
     int aux_rows = 0, aux_dim = 0;
     int aux_out = 0;  // which caller output
     int aux_pitch = 0, aux_lo = 0;
+    int lane = 0;          // 1: runs on the context's side stream (the audio encoder, concurrently with the face encoder)
+    bool join_side = false;  // wait for the side stream before this op
 };
 
 struct Plan {
@@ -168,6 +170,7 @@ struct Plan {
     std::map<int, Act> layer_out;  // layer index -> activation view (debug export)
     long long last_used = 0;       // LRU stamp
     bool x2 = false;               // split-operand precision: activations carry hi and lo planes
+    bool has_side = false;         // some ops run on the side stream
 };
 
 struct w2l_ctx {
@@ -192,6 +195,9 @@ struct w2l_ctx {
     // host-buffer entry points: compute stream + copy streams, double-buffered device staging
     cudaStream_t stream = nullptr;
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_side = nullptr;   // audio-encoder lane of the generator plan
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool use_side = true;            // W2L_DISABLE_SIDESTREAM=1
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -1034,7 +1040,12 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     Act AE;
     CKR(plan_act(pl, &AE, N, 1, 1, 512));
     TmpPool tpa;
+    const size_t audio_first = 0;  // ingest.mel is op 0; ingest.face (op 1) stays on the main lane
     CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.audio_enc, melIn, &tpa, &AE, nullptr));
+    // the audio encoder (small, latency-bound launches) runs on a side stream while the face encoder runs on the main one
+    pl->ops[audio_first].lane = 1;
+    for (size_t i = 2; i < pl->ops.size(); ++i) pl->ops[i].lane = 1;
+    pl->has_side = true;
 
     // face encoder: stage i ends in the skip half of D[6-i] and the next stage reads it from there
     TmpPool tpe;
@@ -1068,6 +1079,7 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     // decoder
     TmpPool tpd;
     x = AE;
+    const size_t dec_first = pl->ops.size();
     for (int k = 0; k < 7; ++k) {
         Act dst = D[k].slice(0, dec_c[k]);
         CKR(emit_chain(ctx, pl, W2L_NET_GENERATOR, g.layers, g.face_dec[k], x, &tpd, &dst, nullptr));
@@ -1078,6 +1090,7 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
     Act none;
     none.N = N; none.H = 96; none.W = 96; none.Cs = 32; none.C = 32;
     CKR(emit_block(ctx, pl, ctx->nets[W2L_NET_GENERATOR], g.output_block0, L, x, none, nullptr, true, T > 0 ? B : N, T > 0 ? T : 1));
+    pl->ops[dec_first].join_side = true;  // the decoder's first block consumes the audio embedding
     return W2L_OK;
 }
 
@@ -1165,7 +1178,18 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
 
 static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, void* out0, void* out1, cudaStream_t st,
                     bool u8 = false) {
+    const bool side = pl->has_side && ctx->use_side;
+    cudaStream_t main_st = st;
+    if (side) {
+        CK(cudaEventRecord(ctx->ev_fork, main_st));
+        CK(cudaStreamWaitEvent(ctx->s_side, ctx->ev_fork, 0));
+    }
     for (Op& op : pl->ops) {
+        if (side && op.join_side) {
+            CK(cudaEventRecord(ctx->ev_join, ctx->s_side));
+            CK(cudaStreamWaitEvent(main_st, ctx->ev_join, 0));
+        }
+        st = (side && op.lane == 1) ? ctx->s_side : main_st;
         switch (op.type) {
             case OP_INGEST: {
                 if (u8 && op.ingest_src == 1) {  // uint8 crops: mask + concat + /255 fused into the ingest
@@ -1359,6 +1383,9 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_h2d, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_d2h, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->s_side, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = cudaEventCreateWithFlags(&ctx->ev_in[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
@@ -1380,6 +1407,8 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_tma_epi = !(e6 && e6[0] == '1');
         const char* e5 = getenv("W2L_DISABLE_MT2");
         ctx->use_mt2 = !(e5 && e5[0] == '1');
+        const char* e8 = getenv("W2L_DISABLE_SIDESTREAM");
+        ctx->use_side = !(e8 && e8[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
         ctx->use_ctfused = !(e4 && e4[0] == '1');
         if (ctx->x2) {  // the split-operand mode runs on the generic kernel with the direct epilogue only
@@ -1411,6 +1440,9 @@ int w2l_destroy(w2l_ctx* ctx) {
     for (int i = 0; i < 6; ++i) if (ctx->stage[i]) cudaFree(ctx->stage[i]);
     if (ctx->s_h2d) cudaStreamDestroy(ctx->s_h2d);
     if (ctx->s_d2h) cudaStreamDestroy(ctx->s_d2h);
+    if (ctx->s_side) cudaStreamDestroy(ctx->s_side);
+    if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+    if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]); }
     if (ctx->mel_tw) cudaFree(ctx->mel_tw);
     if (ctx->mel_bvals) cudaFree(ctx->mel_bvals);
