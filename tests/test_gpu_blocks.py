@@ -18,6 +18,8 @@ REL = 2e-3
 CASES = [
     ("gen 3x3 64 res", "c", 64, 64, 3, 1, 1, 0, True, 2, 24, 24),
     ("gen 3x3 64 96x96", "c", 64, 64, 3, 1, 1, 0, True, 1, 96, 96),
+    ("gen 3x3 64 96x96 res N=5", "c", 64, 64, 3, 1, 1, 0, True, 5, 96, 96),
+    ("3x3 64 lrelu 32x64", "n", 64, 64, 3, 1, 1, 0, False, 19, 32, 64),
     ("gen 1x1 512", "c", 512, 512, 1, 1, 0, 0, False, 5, 1, 1),
     ("gen 3x3 32 res (64B swizzle)", "c", 32, 32, 3, 1, 1, 0, True, 2, 48, 48),
     ("gen 16->32 s2 (32B swizzle)", "c", 16, 32, 3, 2, 1, 0, False, 2, 96, 96),

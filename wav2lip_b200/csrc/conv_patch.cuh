@@ -63,6 +63,7 @@ struct alignas(64) PatchParams {
 
 template <int BN, int BK, bool kBF16, bool kHead>
 __global__ void __launch_bounds__(kPatchThreads, 1) conv_patch_kernel(const __grid_constant__ PatchParams p) {
+    pdl_launch_dependents();
     constexpr int kSlab = BN * BK * 2;  // one (tap, chunk) weight slab
     constexpr int kRowBytes = BK * 2;
     constexpr int kTmemCols = (4 * BN <= 32) ? 32 : (4 * BN <= 64) ? 64 : (4 * BN <= 128) ? 128 : 256;  // 2 tiles in flight x 2 stages
@@ -110,6 +111,7 @@ __global__ void __launch_bounds__(kPatchThreads, 1) conv_patch_kernel(const __gr
     if (warp == 2) tmem_alloc<kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    pdl_wait();  // everything above overlaps the previous kernel's tail; global memory is touched only below
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));

@@ -143,6 +143,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* desc, uint
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
         : "memory");
 }
+// Programmatic dependent launch: the next kernel in the stream may start its prologue (barrier init, TMEM
+// allocation, descriptor prefetch) while this one drains; it touches global memory only after pdl_wait().
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
@@ -343,6 +347,7 @@ __device__ __forceinline__ void epilogue_tile(const EpiParams& e, uint32_t taddr
 // ------------------------------------------------------------------------------------------------
 template <int BN, int BK, bool kBF16, bool kHead, int MT = 1>
 __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_kernel(const __grid_constant__ ConvParams p) {
+    pdl_launch_dependents();
     using Cfg = ConvCfg<BN, BK, MT>;
     constexpr int kStages = Cfg::kStages;
     static_assert(!kHead || BN == 32, "fused head expects the 32-channel output block");
@@ -384,6 +389,7 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
     if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    pdl_wait();  // everything above overlaps the previous kernel's tail; global memory is touched only below
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));

@@ -43,6 +43,7 @@ struct alignas(64) ConvTParams {
 
 template <int BK, bool kBF16>
 __global__ void __launch_bounds__(kCtThreads, 1) convt_fused_kernel(const __grid_constant__ ConvTParams p) {
+    pdl_launch_dependents();
     constexpr int BN = kCtBN;
     constexpr int kRowBytes = BK * 2;
     constexpr int kSlab = BN * BK * 2;
@@ -84,6 +85,7 @@ __global__ void __launch_bounds__(kCtThreads, 1) convt_fused_kernel(const __grid
     if (warp == 2) tmem_alloc<512>(tmem_slot);
     tc_fence_before();
     __syncthreads();
+    pdl_wait();  // everything above overlaps the previous kernel's tail; global memory is touched only below
     tc_fence_after();
     uint32_t tmem_base;
     asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));

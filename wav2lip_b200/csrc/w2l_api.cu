@@ -17,6 +17,7 @@
 #include "../../include/w2l.h"
 #include "aux_kernels.cuh"
 #include "conv_patch.cuh"
+#include "conv_rowpair.cuh"
 #include "conv_tcgen05.cuh"
 #include "convt_fused.cuh"
 #include "mel.cuh"
@@ -150,6 +151,8 @@ struct Op {
     int dyn_smem = 0;
     bool ctf = false;   // convt_fused_kernel
     ConvTParams tp;
+    bool rowpair = false;  // conv_rowpair_kernel
+    RowPairParams rp;
     // ingest
     IngestParams ip;
     int ingest_src = 0;  // which caller tensor: 0 = mel / frames, 1 = face
@@ -186,6 +189,10 @@ struct w2l_ctx {
     bool use_fold_s2 = true;  // W2L_DISABLE_FOLDS2=1
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
+    bool use_pdl = true;      // W2L_DISABLE_PDL=1
+    bool use_rowpair = true;  // W2L_DISABLE_ROWPAIR=1
+    bool use_rowpair64 = false;  // W2L_ROWPAIR64=1: also the 64 -> 64 blocks (slower than the patch kernel there: shared-memory
+                                 // bandwidth, not the tensor pipe, is their limit — DESIGN.md section 3)
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};
@@ -305,6 +312,15 @@ static PatchKernelEntry* find_patch_kernel(int BN, int BK, bool bf16, bool head)
     return nullptr;
 }
 
+typedef void (*RpKernelFn)(const RowPairParams);
+struct RpKernelEntry { int C; bool bf16, head; RpKernelFn fn; bool attr_set; };
+static RpKernelEntry g_rp_kernels[] = {
+    {64, false, false, conv_rowpair_kernel<64, 0, false, false>, false},
+    {64, true, false, conv_rowpair_kernel<64, 0, true, false>, false},
+    {32, false, true, conv_rowpair_kernel<32, 16, false, true>, false},
+    {32, true, true, conv_rowpair_kernel<32, 16, true, true>, false},
+};
+
 typedef void (*CtKernelFn)(const ConvTParams);
 struct CtKernelEntry { int BK; bool bf16; CtKernelFn fn; bool attr_set; };
 static CtKernelEntry g_ct_kernels[] = {
@@ -313,7 +329,26 @@ static CtKernelEntry g_ct_kernels[] = {
 };
 constexpr int kCtSmemMax = 227 * 1024;
 
-static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
+// One launch, optionally with programmatic stream serialization (the kernels call griddepcontrol.wait before they
+// touch global memory, so their prologue overlaps the previous kernel's tail).
+template <typename P>
+static cudaError_t launch_k(void (*fn)(const P), int grid, int block, size_t smem, cudaStream_t st, const P& p, bool pdl) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3((unsigned)block, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, fn, p);
+}
+
+static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st, bool pdl = true) {
+    pdl = pdl && ctx->use_pdl;
     if (op.ctf) {
         CtKernelEntry* e = nullptr;
         for (auto& k : g_ct_kernels) if (k.BK == op.BK && k.bf16 == ctx->bf16) e = &k;
@@ -322,7 +357,19 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
             CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kCtSmemMax));
             e->attr_set = true;
         }
-        e->fn<<<op.grid, kCtThreads, op.dyn_smem, st>>>(op.tp);
+        CK(launch_k(e->fn, op.grid, kCtThreads, op.dyn_smem, st, op.tp, pdl));
+        ctx->launches++;
+        return W2L_OK;
+    }
+    if (op.rowpair) {
+        RpKernelEntry* e = nullptr;
+        for (auto& k : g_rp_kernels) if (k.C == op.BN && k.bf16 == ctx->bf16 && k.head == op.head) e = &k;
+        if (!e) return fail(W2L_EINVAL, "no row-pair kernel for C=%d head=%d", op.BN, (int)op.head);
+        if (!e->attr_set) {
+            CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kSmemExtra));
+            e->attr_set = true;
+        }
+        CK(launch_k(e->fn, op.grid, kRpThreads, op.dyn_smem, st, op.rp, pdl));
         ctx->launches++;
         return W2L_OK;
     }
@@ -333,7 +380,7 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
             CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kSmemExtra));
             e->attr_set = true;
         }
-        e->fn<<<op.grid, kPatchThreads, op.dyn_smem, st>>>(op.pp);
+        CK(launch_k(e->fn, op.grid, kPatchThreads, op.dyn_smem, st, op.pp, pdl));
         ctx->launches++;
         return W2L_OK;
     }
@@ -343,7 +390,7 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st) {
         CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, e->smem));
         e->attr_set = true;
     }
-    e->fn<<<op.grid, e->threads, e->smem, st>>>(op.cp);
+    CK(launch_k(e->fn, op.grid, e->threads, (size_t)e->smem, st, op.cp, pdl));
     ctx->launches++;
     return W2L_OK;
 }
@@ -554,11 +601,94 @@ static int make_patch_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchG
     return W2L_OK;
 }
 
+// The heaviest narrow 3x3 layers: two output rows per GEMM row (conv_rowpair.cuh)
+static bool rowpair_eligible(const w2l_ctx* ctx, const ConvArgs& a, int* tap_of) {
+    if (!ctx->use_rowpair || !ctx->use_patch || ctx->x2) return false;
+    const PackedW& w = *a.w;
+    if (a.sx != 1 || a.sy != 1 || w.ntaps != 9 || w.fold || a.out.f32) return false;
+    if (a.osx != 1 || a.osy != 1) return false;
+    const bool shape64 = ctx->use_rowpair64 && !a.head && a.cout == 64 && w.cin_pad == 64 && w.cout_pad == 64;
+    const bool shape32 = a.head && a.cout == 32 && w.cin_pad == 80 && w.cout_pad == 32;
+    if (!shape64 && !shape32) return false;
+    if (a.in.nwin || a.in.wstride != 1) return false;
+    if (a.Wl % kRpTileW != 0 || a.Hl % kRpTileH != 0) return false;   // 96 x 96 here; ragged tiles would waste the pipe
+    if ((long long)(a.Wl / kRpTileW) * (a.Hl / kRpTileH) * a.in.N < ctx->num_sms / 2) return false;
+    for (int i = 0; i < 9; ++i) tap_of[i] = -1;
+    for (int t = 0; t < 9; ++t) {
+        if (w.dx[t] < -1 || w.dx[t] > 1 || w.dy[t] < -1 || w.dy[t] > 1) return false;
+        tap_of[(w.dx[t] + 1) * 3 + (1 - w.dy[t])] = t;
+    }
+    for (int i = 0; i < 9; ++i) if (tap_of[i] < 0) return false;
+    if (a.res) {
+        if (!shape64) return false;
+        if (a.res->base != a.in.base || a.res->c_off != a.in.c_off || a.res->Cs != a.in.Cs) return false;
+    }
+    return true;
+}
+
+static int make_rowpair_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const int* tap_of) {
+    Op op;
+    op.type = OP_CONV;
+    op.name = a.name + " [rowpair]";
+    op.rowpair = true;
+    op.head = a.head;
+    const PackedW& w = *a.w;
+    const int C = a.cout;
+    op.BN = C; op.BK = 64;
+    RowPairParams& h = op.rp;
+    memset(&h, 0, sizeof(h));
+    CKR(encode_act_map(ctx, &h.tmA0, a.in, 64, kRpPW, kRpPH, 1, 1, 1, a.name.c_str()));
+    CKR(encode_w_map(ctx, &h.tmB0, w, 64, C, a.name.c_str()));
+    if (a.head) {
+        CKR(encode_act_map(ctx, &h.tmA1, a.in, 16, kRpPW, kRpPH, 1, 1, 1, a.name.c_str()));
+        CKR(encode_w_map(ctx, &h.tmB1, w, 16, C, a.name.c_str()));
+    } else {
+        h.tmA1 = h.tmA0; h.tmB1 = h.tmB0;
+    }
+    h.tiles_x = a.Wl / kRpTileW;
+    h.tiles_y = a.Hl / kRpTileH;
+    for (int i = 0; i < 9; ++i) h.tap_of[i] = tap_of[i];
+    h.has_res = a.res ? 1 : 0;
+    const int fixed = a.head ? RowPairCfg<32, 16>::smem_bytes(0, true) : RowPairCfg<64, 0>::smem_bytes(0, false);
+    const int per_stage = a.head ? RowPairCfg<32, 16>::kStageStride : RowPairCfg<64, 0>::kStageStride;
+    h.stages = std::min(kRpMaxStages, (kSmemBudget + kSmemExtra - fixed) / per_stage);
+    op.dyn_smem = fixed + h.stages * per_stage;
+    if (h.stages < 2) return fail(W2L_EINVAL, "%s: row-pair kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
+    fill_epi(&h.ep, a);
+    if (!a.head) {
+        EncodeTiledFn enc = get_encode_fn();
+        const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
+        cuuint64_t strides[3] = {(cuuint64_t)h.ep.out_sx * 2, (cuuint64_t)h.ep.out_sy * 2, (cuuint64_t)h.ep.out_sn * 2};
+        cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)kRpTileW, (cuuint32_t)kRpTileH, 1};
+        cuuint32_t es[4] = {1, 1, 1, 1};
+        CUresult r = enc(&h.tmO, dt, 4, h.ep.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(out) failed with %d", a.name.c_str(), (int)r);
+    } else {
+        h.tmO = h.tmA0;
+    }
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(h.cscale, a.scale + a.ch_off, (size_t)C * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(h.cshift, a.shift + a.ch_off, (size_t)C * 4, cudaMemcpyDeviceToHost));
+    if (a.head) {
+        CK(cudaMemcpy(h.chead_w, a.head_w, 96 * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(h.chead_b, a.head_b, 3 * 4, cudaMemcpyDeviceToHost));
+    }
+    const long long total = (long long)h.tiles_x * h.tiles_y * a.in.N;
+    op.grid = (int)std::min<long long>(total, ctx->num_sms);
+    op.flops = 2.0 * a.macs_per_pixel * (double)a.Wl * a.Hl * a.in.N;
+    pl->ops.push_back(op);
+    return W2L_OK;
+}
+
 static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     if (!get_encode_fn()) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available (no CUDA driver?)");
     const PackedW& w = *a.w;
     if (a.in.C != w.cin_pad) return fail(W2L_EINVAL, "%s: input view has %d channels, weights packed for %d", a.name.c_str(), a.in.C, w.cin_pad);
     if (a.cout % 16 != 0) return fail(W2L_EINVAL, "%s: cout %d not a multiple of 16", a.name.c_str(), a.cout);
+    int rp_taps[9];
+    if (rowpair_eligible(ctx, a, rp_taps)) return make_rowpair_op(ctx, pl, a, rp_taps);
     PatchGeom geom;
     if (patch_eligible(ctx, a, &geom)) return make_patch_op(ctx, pl, a, geom);
     Op op;
@@ -1214,8 +1344,8 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
             }
             case OP_CONV: {
                 if (op.head) {
-                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.pp.ep.head_out = op.cp.ep.head_out;
-                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.pp.ep.head_out_u8 = op.cp.ep.head_out_u8;
+                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.pp.ep.head_out = op.cp.ep.head_out; op.rp.ep.head_out = op.cp.ep.head_out;
+                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.pp.ep.head_out_u8 = op.cp.ep.head_out_u8; op.rp.ep.head_out_u8 = op.cp.ep.head_out_u8;
                 }
                 CKR(launch_conv(ctx, op, st));
                 break;
@@ -1407,6 +1537,12 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_tma_epi = !(e6 && e6[0] == '1');
         const char* e5 = getenv("W2L_DISABLE_MT2");
         ctx->use_mt2 = !(e5 && e5[0] == '1');
+        const char* e9 = getenv("W2L_DISABLE_ROWPAIR");
+        ctx->use_rowpair = !(e9 && e9[0] == '1');
+        const char* e11 = getenv("W2L_DISABLE_PDL");
+        ctx->use_pdl = !(e11 && e11[0] == '1');
+        const char* e10 = getenv("W2L_ROWPAIR64");
+        ctx->use_rowpair64 = (e10 && e10[0] == '1');
         const char* e8 = getenv("W2L_DISABLE_SIDESTREAM");
         ctx->use_side = !(e8 && e8[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
@@ -1772,9 +1908,9 @@ int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, d
     for (Op& op : pl->ops) {
         if (op.type != OP_CONV || k >= cap) continue;
         if (op.head && op.cp.ep.head_out == nullptr && op.pp.ep.head_out == nullptr && op.cp.ep.head_out_u8 == nullptr) continue;
-        CKR(launch_conv(ctx, op, st));  // warm
+        CKR(launch_conv(ctx, op, st, false));  // warm
         CK(cudaEventRecord(e0, st));
-        for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st));
+        for (int i = 0; i < iters; ++i) CKR(launch_conv(ctx, op, st, false));
         CK(cudaEventRecord(e1, st));
         CK(cudaEventSynchronize(e1));
         float ms = 0;
