@@ -14,7 +14,7 @@ barrier and the max-over-ranks time.
 
   value      crops/s with the inputs resident in HBM, CUDA-event time on the launching stream,
              barrier + synchronize on both sides of EXACTLY K steps, max over ranks.
-  e2e        the same metric through the C-ABI host entry point (w2l_generator_forward_host): pinned host
+  e2e        the same metric through the C-ABI host entry points (w2l_generator_submit_host + w2l_host_wait): pinned host
              inputs -> H2D -> forward -> D2H of the (B,3,T,96,96) result, every step.
   roofline   tensor-core bound: algorithmic FLOPs (7.934 GFLOP/crop) of the conv kernel
              launches of one step / their summed per-launch CUDA-event durations (measured live, after the
@@ -190,9 +190,27 @@ def measure_extra(dev):
         for _ in range(10):
             u8_step()
         dt = (time.perf_counter() - t0) / 10
-        out["e2e_u8"] = {"config": "w2l_generator_forward_u8_host: 640 uint8 96x96x3 crops + fp32 mels from pinned host memory, "
-                                   "uint8 predictions back (inference.py:134-140,259-265,269 fused)", "ms": dt * 1e3,
-                         "crops_per_s": n / dt, "h2d_bytes": int(faces.numel() + melh.numel() * 4), "d2h_bytes": int(outh.numel())}
+        outh2 = torch.empty((n, 96, 96, 3), dtype=torch.uint8).pin_memory()
+        outs = [outh, outh2]
+
+        def u8_submit(k):
+            _lib.check(ctx.lib.w2l_generator_submit_u8_host(ctx.h, C.c_void_p(melh.data_ptr()), C.c_void_p(faces.data_ptr()),
+                                                            C.c_void_p(outs[k & 1].data_ptr()), n))
+        for k in range(3):
+            u8_submit(k)
+            _lib.check(ctx.lib.w2l_host_wait(ctx.h, 1))
+        _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
+        t0 = time.perf_counter()
+        for k in range(20):
+            u8_submit(k)
+            _lib.check(ctx.lib.w2l_host_wait(ctx.h, 1))
+        _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
+        dtp = (time.perf_counter() - t0) / 20
+        out["e2e_u8"] = {"config": "640 uint8 96x96x3 crops + fp32 mels from pinned host memory, uint8 predictions back "
+                                   "(inference.py:134-140,259-265,269 fused); submit/wait loop with two batches in flight",
+                         "ms": dtp * 1e3, "crops_per_s": n / dtp, "h2d_bytes": int(faces.numel() + melh.numel() * 4),
+                         "d2h_bytes": int(outh.numel()), "pipelined_equals_sync": bool(torch.equal(outh, outh2)),
+                         "synchronous_call": {"api": "w2l_generator_forward_u8_host", "ms": dt * 1e3, "crops_per_s": n / dt}}
         del g
         # the fp32-faithful precision mode (split fp16 operands, 3 MMAs per product) on the headline workload
         gx = Wav2Lip()
@@ -347,6 +365,7 @@ def main():
         e2e = None
         if not args.no_e2e:
             out_h = torch.empty((B, 3, T, 96, 96), dtype=torch.float32).pin_memory()
+            out_h2 = torch.empty((B, 3, T, 96, 96), dtype=torch.float32).pin_memory()
 
             def e2e_step():
                 _lib.check(ctx.lib.w2l_generator_forward_host(ctx.h, C.c_void_p(mel_h.data_ptr()), C.c_void_p(face_h.data_ptr()),
@@ -358,14 +377,41 @@ def main():
             for _ in range(args.steps):
                 e2e_step()  # synchronous: returns after the D2H copy has landed
             torch.cuda.synchronize(dev)
+            dt_sync = time.perf_counter() - t0
+            dt_sync = max_over_ranks(dt_sync, dev)
+            barrier()
+            ok = bool(torch.equal(out_h.to(dev), out))
+
+            # the serving loop: submit batch k+1 while batch k is in flight (every step still copies its inputs up and its
+            # result down inside the timed region; results land in alternating pinned buffers)
+            outs = [out_h, out_h2]
+
+            def submit(k):
+                _lib.check(ctx.lib.w2l_generator_submit_host(ctx.h, C.c_void_p(mel_h.data_ptr()), C.c_void_p(face_h.data_ptr()),
+                                                             C.c_void_p(outs[k & 1].data_ptr()), B, T))
+            for k in range(3):
+                submit(k)
+                _lib.check(ctx.lib.w2l_host_wait(ctx.h, 1))
+            _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
+            out_h2.zero_()
+            barrier()
+            t0 = time.perf_counter()
+            for k in range(args.steps):
+                submit(k)
+                _lib.check(ctx.lib.w2l_host_wait(ctx.h, 1))   # batch k-1 is complete in host memory here
+            _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
             dt = time.perf_counter() - t0
             dt = max_over_ranks(dt, dev)
             barrier()
-            ok = bool(torch.equal(out_h.to(dev), out))
+            ok = ok and bool(torch.equal(out_h.to(dev), out)) and bool(torch.equal(out_h2.to(dev), out))
             e2e = {"value": world * N * args.steps / dt, "unit": "crops/s",
                    "h2d_bytes_per_step": int(mel_h.numel() * 4 + face_h.numel() * 4),
                    "d2h_bytes_per_step": int(out_h.numel() * 4), "result_matches_device_path": ok,
-                   "api": "w2l_generator_forward_host (pinned host buffers)", "timer": "host wall clock around synchronous calls"}
+                   "api": "w2l_generator_submit_host + w2l_host_wait(1): pinned host buffers, two batches in flight "
+                          "(H2D of step k+1 and D2H of step k-1 overlap the kernels of step k)",
+                   "timer": "host wall clock around the whole loop, drained at the end",
+                   "synchronous_call": {"value": world * N * args.steps / dt_sync, "unit": "crops/s",
+                                        "api": "w2l_generator_forward_host: one blocking call per step, as inference.py:259-265"}}
 
         # ---- roofline: per-launch CUDA-event timing of the conv kernel family (after the timed region) ----
         out = model(mel_d, face_d)  # make the full-batch plan the profiled one again (the host path runs chunk plans)

@@ -99,6 +99,17 @@ int w2l_generator_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_
 int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_host, const float* face_host,
                                float* out_host, int B, int T);
 
+/* Asynchronous form of the two host-buffer calls, for a serving loop that keeps the PCIe link and the GPU busy at
+ * the same time (the reference's loop, inference.py:259-265, is copy -> forward -> copy, strictly serial):
+ *   w2l_generator_submit_host / _submit_u8_host enqueue H2D -> forward -> D2H for one batch and return at once;
+ *   at most two submissions are in flight (a third call first waits for the oldest);
+ *   w2l_host_wait(ctx, keep) blocks until at most `keep` submissions are still in flight — their out_host buffers are
+ *   complete when it returns, in submission order.  Host buffers must stay valid (and should be pinned) until retired.
+ *       submit(batch 0); for k = 1..: submit(batch k); w2l_host_wait(ctx, 1); consume(batch k-1); ... w2l_host_wait(ctx, 0) */
+int w2l_generator_submit_host(w2l_ctx* ctx, const float* mel_host, const float* face_host, float* out_host, int B, int T);
+int w2l_generator_submit_u8_host(w2l_ctx* ctx, const float* mel_host, const uint8_t* faces_host, uint8_t* out_host, int N);
+int w2l_host_wait(w2l_ctx* ctx, int keep_in_flight);
+
 /* Scope row (f): the batch assembly around the generator call of inference.py, fused on the GPU.
  * Replaces inference.py:134-140 (mask the lower half, concat [masked | full] on channels, /255, NHWC->NCHW),
  * :259-263 (to device, forward) and :265,:269 (transpose, *255., astype(uint8)) — everything between the

@@ -86,6 +86,66 @@ def test_host_entry_point_matches_device_path(B, T):
     assert torch.equal(out_p, y_dev)
 
 
+def test_submit_wait_pipeline_matches_device_path():
+    """w2l_generator_submit_host / _submit_u8_host + w2l_host_wait: results land in submission order and equal the
+    device path bit for bit, across changing batch sizes (staging buffers grow -> the pipeline drains first)."""
+    from wav2lip_b200 import _lib
+    import ctypes as C
+    g = _fresh_generator({})
+    ctx = g._w2l_ctx
+    sizes = [3, 70, 5, 5, 130, 1]
+    batches, refs, outs = [], [], []
+    for i, n in enumerate(sizes):
+        mel, face = O.make_generator_inputs(n, seed=100 + i)
+        with torch.no_grad():
+            refs.append(g(mel.cuda(), face.cuda()).cpu())
+        batches.append((mel.contiguous().pin_memory(), face.contiguous().pin_memory()))
+        outs.append(torch.zeros_like(refs[-1]).pin_memory())
+    done = 0
+    for i, n in enumerate(sizes):
+        _lib.check(ctx.lib.w2l_generator_submit_host(ctx.h, C.c_void_p(batches[i][0].data_ptr()), C.c_void_p(batches[i][1].data_ptr()),
+                                                     C.c_void_p(outs[i].data_ptr()), n, 0))
+        _lib.check(ctx.lib.w2l_host_wait(ctx.h, 1))
+        while done < i:   # everything but the newest submission is complete
+            assert torch.equal(outs[done], refs[done]), done
+            done += 1
+    _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
+    assert torch.equal(outs[-1], refs[-1])
+    # three submissions without a wait: the third one retires the first by itself
+    for o in outs[:3]:
+        o.zero_()
+    for i in range(3):
+        _lib.check(ctx.lib.w2l_generator_submit_host(ctx.h, C.c_void_p(batches[i][0].data_ptr()), C.c_void_p(batches[i][1].data_ptr()),
+                                                     C.c_void_p(outs[i].data_ptr()), sizes[i], 0))
+    _lib.check(ctx.lib.w2l_host_wait(ctx.h, 0))
+    for i in range(3):
+        assert torch.equal(outs[i], refs[i])
+    # a synchronous call after asynchronous ones
+    _lib.check(ctx.lib.w2l_generator_submit_host(ctx.h, C.c_void_p(batches[1][0].data_ptr()), C.c_void_p(batches[1][1].data_ptr()),
+                                                 C.c_void_p(outs[1].data_ptr()), sizes[1], 0))
+    o2 = torch.zeros_like(refs[4]).pin_memory()
+    _lib.check(ctx.lib.w2l_generator_forward_host(ctx.h, C.c_void_p(batches[4][0].data_ptr()), C.c_void_p(batches[4][1].data_ptr()),
+                                                  C.c_void_p(o2.data_ptr()), sizes[4], 0))
+    assert torch.equal(o2, refs[4]) and torch.equal(outs[1], refs[1])
+
+
+def test_infer_stream_fp32_and_u8():
+    g = _fresh_generator({})
+    gen = torch.Generator().manual_seed(5)
+    f32 = [O.make_generator_inputs(n, seed=200 + n) for n in (4, 9, 2)]
+    with torch.no_grad():
+        refs = [g(m.cuda(), f.cuda()).cpu() for m, f in f32]
+    got = list(g.infer_stream(iter(f32)))
+    assert len(got) == 3 and all(torch.equal(a, b) for a, b in zip(got, refs))
+    u8 = [((torch.rand((n, 1, 80, 16), generator=gen) * 8 - 4), torch.randint(0, 256, (n, 96, 96, 3), generator=gen, dtype=torch.uint8))
+          for n in (6, 1, 11)]
+    with torch.no_grad():
+        refs8 = [g.infer_u8(m.cuda(), f.cuda()).cpu() for m, f in u8]
+    got8 = list(g.infer_stream(iter(u8)))
+    assert len(got8) == 3 and all(torch.equal(a, b) for a, b in zip(got8, refs8))
+    assert list(g.infer_stream(iter([]))) == []
+
+
 def test_launch_counter_and_profile():
     from wav2lip_b200 import _lib
     g = _fresh_generator({})

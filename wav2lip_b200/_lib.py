@@ -22,6 +22,7 @@ EXPORTS = [
     "w2l_abi_version", "w2l_last_error", "w2l_net_num_layers", "w2l_net_layer_info",
     "w2l_create", "w2l_destroy", "w2l_load_weights",
     "w2l_generator_forward", "w2l_generator_forward_host", "w2l_generator_forward_u8", "w2l_generator_forward_u8_host",
+    "w2l_generator_submit_host", "w2l_generator_submit_u8_host", "w2l_host_wait",
     "w2l_syncnet_forward", "w2l_disc_forward",
     "w2l_conv_block_forward", "w2l_debug_layer_output",
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
@@ -69,6 +70,9 @@ def get_lib() -> C.CDLL:
     lib.w2l_generator_forward_host.argtypes = [vp, vp, vp, vp, i32, i32]
     lib.w2l_generator_forward_u8.argtypes = [vp, vp, vp, vp, i32, vp]
     lib.w2l_generator_forward_u8_host.argtypes = [vp, vp, vp, vp, i32]
+    lib.w2l_generator_submit_host.argtypes = [vp, vp, vp, vp, i32, i32]
+    lib.w2l_generator_submit_u8_host.argtypes = [vp, vp, vp, vp, i32]
+    lib.w2l_host_wait.argtypes = [vp, i32]
     lib.w2l_mel_num_chunks.argtypes = [i64, C.c_double]
     lib.w2l_mel_num_chunks.restype = i64
     lib.w2l_mel_chunks.argtypes = [vp, vp, i64, C.c_double, vp, i64, vp]

@@ -207,6 +207,8 @@ struct w2l_ctx {
     bool use_side = true;            // W2L_DISABLE_SIDESTREAM=1
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    long long host_seq = 0;   // host-buffer submissions so far (staging slot = seq & 1)
+    int host_inflight = 0;    // submitted and not yet retired by host_drain
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
     // mel tables
     double2* mel_tw = nullptr;
@@ -1655,43 +1657,91 @@ int w2l_generator_forward(w2l_ctx* ctx, const float* mel, const float* face, flo
     return run_plan(ctx, pl, mel, face, out, nullptr, (cudaStream_t)stream);
 }
 
+// ---- host-buffer entry points: a two-slot software pipeline over three streams --------------------------------
+// Every submission (a whole call, or one chunk of a synchronous call) goes H2D (s_h2d) -> kernels (ctx->stream) ->
+// D2H (s_d2h) through device staging slot seq & 1, so the copies of one submission overlap the kernels of its
+// neighbours.  At most two submissions are in flight.
+static int host_drain(w2l_ctx* ctx, int keep) {
+    while (ctx->host_inflight > keep) {
+        const long long oldest = ctx->host_seq - ctx->host_inflight;
+        CK(cudaEventSynchronize(ctx->ev_out[oldest & 1]));
+        ctx->host_inflight--;
+    }
+    return W2L_OK;
+}
+
+static int host_submit(w2l_ctx* ctx, int B, int T, const void* mel_h, size_t mel_bytes, const void* face_h, size_t face_bytes,
+                       void* out_h, size_t out_bytes, bool u8) {
+    if (ctx->host_inflight >= 2) CKR(host_drain(ctx, 1));
+    const int sl = (int)(ctx->host_seq & 1);
+    if (ctx->stage_bytes[0 + sl] < mel_bytes || ctx->stage_bytes[2 + sl] < face_bytes || ctx->stage_bytes[4 + sl] < out_bytes) {
+        CKR(host_drain(ctx, 0));  // growing a staging buffer frees the old one
+        CKR(ensure_stage(ctx, 0 + sl, mel_bytes));
+        CKR(ensure_stage(ctx, 2 + sl, face_bytes));
+        CKR(ensure_stage(ctx, 4 + sl, out_bytes));
+    }
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_GENERATOR, B, T, &pl));
+    // (waiting on an event that was never recorded is a no-op)
+    CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));   // the kernels that read staging_in[sl] two submissions ago
+    CK(cudaMemcpyAsync(ctx->stage[0 + sl], mel_h, mel_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaMemcpyAsync(ctx->stage[2 + sl], face_h, face_bytes, cudaMemcpyHostToDevice, ctx->s_h2d));
+    CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_h2d));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
+    CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));   // staging_out[sl] drained
+    CKR(run_plan(ctx, pl, ctx->stage[0 + sl], ctx->stage[2 + sl], ctx->stage[4 + sl], nullptr, ctx->stream, u8));
+    CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
+    CK(cudaMemcpyAsync(out_h, ctx->stage[4 + sl], out_bytes, cudaMemcpyDeviceToHost, ctx->s_d2h));
+    CK(cudaEventRecord(ctx->ev_out[sl], ctx->s_d2h));
+    ctx->host_seq++;
+    ctx->host_inflight++;
+    return W2L_OK;
+}
+
+static int host_chunks(int B) {
+    int n = B >= 64 ? 2 : 1;  // fewer, larger chunks: small batches run the low-resolution layers inefficiently
+    if (const char* ev = getenv("W2L_HOST_CHUNKS")) n = std::max(1, std::min(atoi(ev), B));
+    return n;
+}
+
 int w2l_generator_forward_host(w2l_ctx* ctx, const float* mel_h, const float* face_h, float* out_h, int B, int T) {
     if (!ctx || !mel_h || !face_h || !out_h) return fail(W2L_EINVAL, "null argument");
     if (B <= 0 || T < 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
     DeviceGuard g(ctx->device);
-    // The batch is cut along B into up to 4 chunks (whole T-windows, so every chunk is itself a legal call) and
-    // software-pipelined over three streams: H2D of chunk i+1 and D2H of chunk i-1 overlap the kernels of chunk i.
+    // A synchronous call cuts the batch along B (whole T-windows, so every chunk is itself a legal call) so that the
+    // copies of one chunk overlap the kernels of the other.
     const int tt = T > 0 ? T : 1;
-    int nchunks = B >= 64 ? 2 : 1;  // fewer, larger chunks: small batches run the low-resolution layers inefficiently
-    if (const char* ev = getenv("W2L_HOST_CHUNKS")) nchunks = std::max(1, std::min(atoi(ev), B));
-    const int cb = (B + nchunks - 1) / nchunks;
+    const int cb = (B + host_chunks(B) - 1) / host_chunks(B);
     const size_t per_b_mel = (size_t)tt * 1280 * 4, per_b_face = (size_t)tt * 6 * 9216 * 4, per_b_out = (size_t)tt * 3 * 9216 * 4;
-    for (int i = 0; i < 2; ++i) {
-        CKR(ensure_stage(ctx, 0 + i, cb * per_b_mel));
-        CKR(ensure_stage(ctx, 2 + i, cb * per_b_face));
-        CKR(ensure_stage(ctx, 4 + i, cb * per_b_out));
-    }
-    int k = 0;
-    for (int b0 = 0; b0 < B; b0 += cb, ++k) {
+    for (int b0 = 0; b0 < B; b0 += cb) {
         const int bc = std::min(cb, B - b0);
-        const int sl = k & 1;
-        Plan* pl;
-        CKR(get_plan(ctx, W2L_NET_GENERATOR, bc, T, &pl));
-        if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));  // staging_in[sl] free again
-        CK(cudaMemcpyAsync(ctx->stage[0 + sl], (const char*)mel_h + b0 * per_b_mel, bc * per_b_mel, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CK(cudaMemcpyAsync(ctx->stage[2 + sl], (const char*)face_h + b0 * per_b_face, bc * per_b_face, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_h2d));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
-        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));  // staging_out[sl] drained
-        CKR(run_plan(ctx, pl, ctx->stage[0 + sl], ctx->stage[2 + sl], ctx->stage[4 + sl], nullptr, ctx->stream));
-        CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
-        CK(cudaMemcpyAsync((char*)out_h + b0 * per_b_out, ctx->stage[4 + sl], bc * per_b_out, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        CK(cudaEventRecord(ctx->ev_out[sl], ctx->s_d2h));
+        CKR(host_submit(ctx, bc, T, (const char*)mel_h + b0 * per_b_mel, bc * per_b_mel, (const char*)face_h + b0 * per_b_face,
+                        bc * per_b_face, (char*)out_h + b0 * per_b_out, bc * per_b_out, false));
     }
-    CK(cudaStreamSynchronize(ctx->s_d2h));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return W2L_OK;
+    return host_drain(ctx, 0);
+}
+
+int w2l_generator_submit_host(w2l_ctx* ctx, const float* mel_h, const float* face_h, float* out_h, int B, int T) {
+    if (!ctx || !mel_h || !face_h || !out_h) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || T < 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
+    DeviceGuard g(ctx->device);
+    const size_t n = (size_t)B * (T > 0 ? T : 1);
+    return host_submit(ctx, B, T, mel_h, n * 1280 * 4, face_h, n * 6 * 9216 * 4, out_h, n * 3 * 9216 * 4, false);
+}
+
+int w2l_generator_submit_u8_host(w2l_ctx* ctx, const float* mel_h, const uint8_t* faces_h, uint8_t* out_h, int N) {
+    if (!ctx || !mel_h || !faces_h || !out_h) return fail(W2L_EINVAL, "null argument");
+    if (N <= 0) return fail(W2L_EINVAL, "bad batch %d", N);
+    DeviceGuard g(ctx->device);
+    return host_submit(ctx, N, 0, mel_h, (size_t)N * 1280 * 4, faces_h, (size_t)N * 96 * 96 * 3, out_h, (size_t)N * 96 * 96 * 3, true);
+}
+
+int w2l_host_wait(w2l_ctx* ctx, int keep_in_flight) {
+    if (!ctx) return fail(W2L_EINVAL, "null argument");
+    if (keep_in_flight < 0) keep_in_flight = 0;
+    DeviceGuard g(ctx->device);
+    return host_drain(ctx, keep_in_flight);
 }
 
 int w2l_generator_forward_u8(w2l_ctx* ctx, const float* mel, const uint8_t* faces, uint8_t* out, int N, void* stream) {
@@ -1707,36 +1757,14 @@ int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_h, const uint8_
     if (!ctx || !mel_h || !faces_h || !out_h) return fail(W2L_EINVAL, "null argument");
     if (N <= 0) return fail(W2L_EINVAL, "bad batch %d", N);
     DeviceGuard g(ctx->device);
-    int nchunks = N >= 64 ? 2 : 1;
-    if (const char* ev = getenv("W2L_HOST_CHUNKS")) nchunks = std::max(1, std::min(atoi(ev), N));
-    const int cb = (N + nchunks - 1) / nchunks;
+    const int cb = (N + host_chunks(N) - 1) / host_chunks(N);
     const size_t per_mel = 1280 * 4, per_face = 96 * 96 * 3, per_out = 96 * 96 * 3;
-    for (int i = 0; i < 2; ++i) {
-        CKR(ensure_stage(ctx, 0 + i, cb * per_mel));
-        CKR(ensure_stage(ctx, 2 + i, cb * per_face));
-        CKR(ensure_stage(ctx, 4 + i, cb * per_out));
-    }
-    int k = 0;
-    for (int b0 = 0; b0 < N; b0 += cb, ++k) {
+    for (int b0 = 0; b0 < N; b0 += cb) {
         const int bc = std::min(cb, N - b0);
-        const int sl = k & 1;
-        Plan* pl;
-        CKR(get_plan(ctx, W2L_NET_GENERATOR, bc, 0, &pl));
-        if (k >= 2) CK(cudaStreamWaitEvent(ctx->s_h2d, ctx->ev_done[sl], 0));
-        CK(cudaMemcpyAsync(ctx->stage[0 + sl], (const char*)mel_h + b0 * per_mel, bc * per_mel, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CK(cudaMemcpyAsync(ctx->stage[2 + sl], (const char*)faces_h + b0 * per_face, bc * per_face, cudaMemcpyHostToDevice, ctx->s_h2d));
-        CK(cudaEventRecord(ctx->ev_in[sl], ctx->s_h2d));
-        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_in[sl], 0));
-        if (k >= 2) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_out[sl], 0));
-        CKR(run_plan(ctx, pl, ctx->stage[0 + sl], ctx->stage[2 + sl], ctx->stage[4 + sl], nullptr, ctx->stream, true));
-        CK(cudaEventRecord(ctx->ev_done[sl], ctx->stream));
-        CK(cudaStreamWaitEvent(ctx->s_d2h, ctx->ev_done[sl], 0));
-        CK(cudaMemcpyAsync((char*)out_h + b0 * per_out, ctx->stage[4 + sl], bc * per_out, cudaMemcpyDeviceToHost, ctx->s_d2h));
-        CK(cudaEventRecord(ctx->ev_out[sl], ctx->s_d2h));
+        CKR(host_submit(ctx, bc, 0, (const char*)mel_h + b0 * per_mel, bc * per_mel, faces_h + b0 * per_face, bc * per_face,
+                        out_h + b0 * per_out, bc * per_out, true));
     }
-    CK(cudaStreamSynchronize(ctx->s_d2h));
-    CK(cudaStreamSynchronize(ctx->stream));
-    return W2L_OK;
+    return host_drain(ctx, 0);
 }
 
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float* a_emb, float* v_emb, int B, void* stream) {
