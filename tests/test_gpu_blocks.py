@@ -24,6 +24,7 @@ CASES = [
     ("gen 3x3 32 res (64B swizzle)", "c", 32, 32, 3, 1, 1, 0, True, 2, 48, 48),
     ("gen 16->32 s2 (32B swizzle)", "c", 16, 32, 3, 2, 1, 0, False, 2, 96, 96),
     ("gen 7x7 6->16", "c", 6, 16, 7, 1, 3, 0, False, 2, 96, 96),
+    ("gen 7x7 6->16 N=5 (row-stack kernel)", "c", 6, 16, 7, 1, 3, 0, False, 5, 96, 96),
     ("gen 3x3 128 res", "c", 128, 128, 3, 1, 1, 0, True, 3, 12, 12),
     ("gen 3x3 256 res", "c", 256, 256, 3, 1, 1, 0, True, 3, 6, 6),
     ("gen 3x3 384 res", "c", 384, 384, 3, 1, 1, 0, True, 2, 12, 12),

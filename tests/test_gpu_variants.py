@@ -14,13 +14,13 @@ from oracle import w2l_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED", "W2L_DISABLE_MT2", "W2L_DISABLE_TMAEPI", "W2L_DISABLE_FOLDS2", "W2L_DISABLE_ROWPAIR",
+FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED", "W2L_DISABLE_MT2", "W2L_DISABLE_TMAEPI", "W2L_DISABLE_FOLDS2", "W2L_DISABLE_ROWSTACK",
          "W2L_DISABLE_SIDESTREAM"]
 
 
 def _fresh_generator(env):
     from wav2lip_b200.models import Wav2Lip
-    keys = FLAGS + ["W2L_ROWPAIR64"]
+    keys = FLAGS
     old = {k: os.environ.get(k) for k in keys}
     try:
         for k in keys:
@@ -41,8 +41,8 @@ def _fresh_generator(env):
 
 
 @pytest.mark.parametrize("env", [{}, {"W2L_DISABLE_HALO": "1"}, {"W2L_DISABLE_FOLD": "1"},
-                                 {"W2L_DISABLE_CTFUSED": "1"}, {"W2L_DISABLE_ROWPAIR": "1"}, {"W2L_ROWPAIR64": "1"}, {k: "1" for k in FLAGS}],
-                         ids=["all-on", "no-patch", "no-fold", "no-fused-convT", "no-rowpair", "rowpair-64", "generic-only"])
+                                 {"W2L_DISABLE_CTFUSED": "1"}, {"W2L_DISABLE_ROWSTACK": "1"}, {k: "1" for k in FLAGS}],
+                         ids=["all-on", "no-patch", "no-fold", "no-fused-convT", "no-rowstack", "generic-only"])
 def test_generator_variants_agree_with_oracle(env, golden_dir):
     gold = np.load(os.path.join(golden_dir, "generator.npz"))
     g = _fresh_generator(env)

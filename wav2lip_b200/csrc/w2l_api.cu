@@ -17,7 +17,7 @@
 #include "../../include/w2l.h"
 #include "aux_kernels.cuh"
 #include "conv_patch.cuh"
-#include "conv_rowpair.cuh"
+#include "conv_rowstack.cuh"
 #include "conv_tcgen05.cuh"
 #include "convt_fused.cuh"
 #include "mel.cuh"
@@ -151,8 +151,9 @@ struct Op {
     int dyn_smem = 0;
     bool ctf = false;   // convt_fused_kernel
     ConvTParams tp;
-    bool rowpair = false;  // conv_rowpair_kernel
-    RowPairParams rp;
+    bool rowstack = false;  // conv_rowstack_kernel
+    int rs_shape = 0;       // 0: output block (C=32, S=2, 3x3, head)   1: folded 7-row first block (C=16, S=3)
+    RowStackParams rs;
     // ingest
     IngestParams ip;
     int ingest_src = 0;  // which caller tensor: 0 = mel / frames, 1 = face
@@ -190,9 +191,7 @@ struct w2l_ctx {
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     bool use_pdl = true;      // W2L_DISABLE_PDL=1
-    bool use_rowpair = true;  // W2L_DISABLE_ROWPAIR=1
-    bool use_rowpair64 = false;  // W2L_ROWPAIR64=1: also the 64 -> 64 blocks (slower than the patch kernel there: shared-memory
-                                 // bandwidth, not the tensor pipe, is their limit — DESIGN.md section 3)
+    bool use_rowstack = true;  // W2L_DISABLE_ROWSTACK=1
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};
@@ -314,14 +313,16 @@ static PatchKernelEntry* find_patch_kernel(int BN, int BK, bool bf16, bool head)
     return nullptr;
 }
 
-typedef void (*RpKernelFn)(const RowPairParams);
-struct RpKernelEntry { int C; bool bf16, head; RpKernelFn fn; bool attr_set; };
-static RpKernelEntry g_rp_kernels[] = {
-    {64, false, false, conv_rowpair_kernel<64, 0, false, false>, false},
-    {64, true, false, conv_rowpair_kernel<64, 0, true, false>, false},
-    {32, false, true, conv_rowpair_kernel<32, 16, false, true>, false},
-    {32, true, true, conv_rowpair_kernel<32, 16, true, true>, false},
+typedef void (*RsKernelFn)(const RowStackParams);
+struct RsKernelEntry { int shape; bool bf16; RsKernelFn fn; bool attr_set; };
+static RsKernelEntry g_rs_kernels[] = {
+    {0, false, conv_rowstack_kernel<32, 2, 3, 3, 16, false, true>, false},
+    {0, true, conv_rowstack_kernel<32, 2, 3, 3, 16, true, true>, false},
+    {1, false, conv_rowstack_kernel<16, 3, 7, 1, 0, false, false>, false},
+    {1, true, conv_rowstack_kernel<16, 3, 7, 1, 0, true, false>, false},
 };
+using RsCfg0 = RowStackCfg<32, 2, 3, 3, 16>;
+using RsCfg1 = RowStackCfg<16, 3, 7, 1, 0>;
 
 typedef void (*CtKernelFn)(const ConvTParams);
 struct CtKernelEntry { int BK; bool bf16; CtKernelFn fn; bool attr_set; };
@@ -363,15 +364,15 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st, bool pdl = t
         ctx->launches++;
         return W2L_OK;
     }
-    if (op.rowpair) {
-        RpKernelEntry* e = nullptr;
-        for (auto& k : g_rp_kernels) if (k.C == op.BN && k.bf16 == ctx->bf16 && k.head == op.head) e = &k;
-        if (!e) return fail(W2L_EINVAL, "no row-pair kernel for C=%d head=%d", op.BN, (int)op.head);
+    if (op.rowstack) {
+        RsKernelEntry* e = nullptr;
+        for (auto& k : g_rs_kernels) if (k.shape == op.rs_shape && k.bf16 == ctx->bf16) e = &k;
+        if (!e) return fail(W2L_EINVAL, "no row-stack kernel for shape %d", op.rs_shape);
         if (!e->attr_set) {
             CK(cudaFuncSetAttribute(e->fn, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget + kSmemExtra));
             e->attr_set = true;
         }
-        CK(launch_k(e->fn, op.grid, kRpThreads, op.dyn_smem, st, op.rp, pdl));
+        CK(launch_k(e->fn, op.grid, kRsThreads, op.dyn_smem, st, op.rs, pdl));
         ctx->launches++;
         return W2L_OK;
     }
@@ -603,73 +604,77 @@ static int make_patch_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const PatchG
     return W2L_OK;
 }
 
-// The heaviest narrow 3x3 layers: two output rows per GEMM row (conv_rowpair.cuh)
-static bool rowpair_eligible(const w2l_ctx* ctx, const ConvArgs& a, int* tap_of) {
-    if (!ctx->use_rowpair || !ctx->use_patch || ctx->x2) return false;
+// The narrowest 96 x 96 layers: S output rows per GEMM row (conv_rowstack.cuh).  Returns the shape id or -1.
+static int rowstack_eligible(const w2l_ctx* ctx, const ConvArgs& a, int* tap_of) {
+    if (!ctx->use_rowstack || !ctx->use_patch || ctx->x2) return -1;
     const PackedW& w = *a.w;
-    if (a.sx != 1 || a.sy != 1 || w.ntaps != 9 || w.fold || a.out.f32) return false;
-    if (a.osx != 1 || a.osy != 1) return false;
-    const bool shape64 = ctx->use_rowpair64 && !a.head && a.cout == 64 && w.cin_pad == 64 && w.cout_pad == 64;
-    const bool shape32 = a.head && a.cout == 32 && w.cin_pad == 80 && w.cout_pad == 32;
-    if (!shape64 && !shape32) return false;
-    if (a.in.nwin || a.in.wstride != 1) return false;
-    if (a.Wl % kRpTileW != 0 || a.Hl % kRpTileH != 0) return false;   // 96 x 96 here; ragged tiles would waste the pipe
-    if ((long long)(a.Wl / kRpTileW) * (a.Hl / kRpTileH) * a.in.N < ctx->num_sms / 2) return false;
-    for (int i = 0; i < 9; ++i) tap_of[i] = -1;
-    for (int t = 0; t < 9; ++t) {
-        if (w.dx[t] < -1 || w.dx[t] > 1 || w.dy[t] < -1 || w.dy[t] > 1) return false;
-        tap_of[(w.dx[t] + 1) * 3 + (1 - w.dy[t])] = t;
+    if (a.sx != 1 || a.sy != 1 || a.osx != 1 || a.osy != 1 || a.out.f32 || a.res) return -1;
+    int shape = -1;
+    if (a.head && a.cout == 32 && w.cin_pad == 80 && w.cout_pad == 32 && w.ntaps == 9 && !w.fold && !a.in.nwin && a.in.wstride == 1) shape = 0;
+    if (!a.head && a.cout == 16 && w.cout_pad == 16 && w.fold && w.ntaps == 7 && w.cin_pad == 64 && a.in.wstride == 1) shape = 1;
+    if (shape < 0) return -1;
+    const int tile_h = shape == 0 ? RsCfg0::kTileH : RsCfg1::kTileH;
+    const int R = shape == 0 ? 1 : 3, ndx = shape == 0 ? 3 : 1, ty = 2 * R + 1;
+    if (a.Wl % kRsTileW != 0 || a.Hl % tile_h != 0) return -1;   // 96 x 96 here; ragged tiles would waste the pipe
+    if ((long long)(a.Wl / kRsTileW) * (a.Hl / tile_h) * a.in.N < ctx->num_sms / 2) return -1;
+    for (int i = 0; i < ndx * ty; ++i) tap_of[i] = -1;
+    for (int t = 0; t < w.ntaps; ++t) {
+        const int dx = w.dx[t], dy = w.dy[t];
+        if (dy < -R || dy > R || (ndx == 1 ? dx != 0 : (dx < -1 || dx > 1))) return -1;
+        tap_of[(ndx == 1 ? 0 : dx + 1) * ty + (R - dy)] = t;
     }
-    for (int i = 0; i < 9; ++i) if (tap_of[i] < 0) return false;
-    if (a.res) {
-        if (!shape64) return false;
-        if (a.res->base != a.in.base || a.res->c_off != a.in.c_off || a.res->Cs != a.in.Cs) return false;
-    }
-    return true;
+    for (int i = 0; i < ndx * ty; ++i) if (tap_of[i] < 0) return -1;
+    return shape;
 }
 
-static int make_rowpair_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, const int* tap_of) {
+static int make_rowstack_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, int shape, const int* tap_of) {
     Op op;
     op.type = OP_CONV;
-    op.name = a.name + " [rowpair]";
-    op.rowpair = true;
+    op.name = a.name + (shape == 0 ? " [rowstack x2]" : " [fold+rowstack x3]");
+    op.rowstack = true;
+    op.rs_shape = shape;
     op.head = a.head;
     const PackedW& w = *a.w;
     const int C = a.cout;
     op.BN = C; op.BK = 64;
-    RowPairParams& h = op.rp;
+    RowStackParams& h = op.rs;
     memset(&h, 0, sizeof(h));
-    CKR(encode_act_map(ctx, &h.tmA0, a.in, 64, kRpPW, kRpPH, 1, 1, 1, a.name.c_str()));
+    const int PW = shape == 0 ? RsCfg0::PW : RsCfg1::PW, PH = shape == 0 ? RsCfg0::PH : RsCfg1::PH;
+    const int tile_h = shape == 0 ? RsCfg0::kTileH : RsCfg1::kTileH;
+    CKR(encode_act_map(ctx, &h.tmA0, a.in, 64, PW, PH, 1, 1, 1, a.name.c_str()));
     CKR(encode_w_map(ctx, &h.tmB0, w, 64, C, a.name.c_str()));
-    if (a.head) {
-        CKR(encode_act_map(ctx, &h.tmA1, a.in, 16, kRpPW, kRpPH, 1, 1, 1, a.name.c_str()));
+    if (shape == 0) {
+        CKR(encode_act_map(ctx, &h.tmA1, a.in, 16, PW, PH, 1, 1, 1, a.name.c_str()));
         CKR(encode_w_map(ctx, &h.tmB1, w, 16, C, a.name.c_str()));
     } else {
         h.tmA1 = h.tmA0; h.tmB1 = h.tmB0;
     }
-    h.tiles_x = a.Wl / kRpTileW;
-    h.tiles_y = a.Hl / kRpTileH;
-    for (int i = 0; i < 9; ++i) h.tap_of[i] = tap_of[i];
-    h.has_res = a.res ? 1 : 0;
-    const int fixed = a.head ? RowPairCfg<32, 16>::smem_bytes(0, true) : RowPairCfg<64, 0>::smem_bytes(0, false);
-    const int per_stage = a.head ? RowPairCfg<32, 16>::kStageStride : RowPairCfg<64, 0>::kStageStride;
-    h.stages = std::min(kRpMaxStages, (kSmemBudget + kSmemExtra - fixed) / per_stage);
+    h.tiles_x = a.Wl / kRsTileW;
+    h.tiles_y = a.Hl / tile_h;
+    h.ox = shape == 0 ? -1 : 0;   // folded inputs: the window already starts at the leftmost tap
+    h.oy = shape == 0 ? -1 : -3;
+    for (int i = 0; i < (shape == 0 ? 9 : 7); ++i) h.tap_of[i] = tap_of[i];
+    const int fixed = shape == 0 ? RsCfg0::smem_bytes(0, true) : RsCfg1::smem_bytes(0, false);
+    const int per_stage = shape == 0 ? RsCfg0::kStageStride : RsCfg1::kStageStride;
+    h.stages = std::min(kRsMaxStages, (kSmemBudget + kSmemExtra - fixed) / per_stage);
     op.dyn_smem = fixed + h.stages * per_stage;
-    if (h.stages < 2) return fail(W2L_EINVAL, "%s: row-pair kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
+    if (h.stages < 2) return fail(W2L_EINVAL, "%s: row-stack kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
     fill_epi(&h.ep, a);
     if (!a.head) {
         EncodeTiledFn enc = get_encode_fn();
         const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+        const CUtensorMapSwizzle sw = C == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : C == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
         cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
         cuuint64_t strides[3] = {(cuuint64_t)h.ep.out_sx * 2, (cuuint64_t)h.ep.out_sy * 2, (cuuint64_t)h.ep.out_sn * 2};
-        cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)kRpTileW, (cuuint32_t)kRpTileH, 1};
+        cuuint32_t box[4] = {(cuuint32_t)C, (cuuint32_t)kRsTileW, (cuuint32_t)tile_h, 1};
         cuuint32_t es[4] = {1, 1, 1, 1};
-        CUresult r = enc(&h.tmO, dt, 4, h.ep.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+        CUresult r = enc(&h.tmO, dt, 4, h.ep.out, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "%s: cuTensorMapEncodeTiled(out) failed with %d", a.name.c_str(), (int)r);
     } else {
         h.tmO = h.tmA0;
     }
+    h.tmO2 = h.tmO;
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(h.cscale, a.scale + a.ch_off, (size_t)C * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(h.cshift, a.shift + a.ch_off, (size_t)C * 4, cudaMemcpyDeviceToHost));
@@ -689,8 +694,9 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     const PackedW& w = *a.w;
     if (a.in.C != w.cin_pad) return fail(W2L_EINVAL, "%s: input view has %d channels, weights packed for %d", a.name.c_str(), a.in.C, w.cin_pad);
     if (a.cout % 16 != 0) return fail(W2L_EINVAL, "%s: cout %d not a multiple of 16", a.name.c_str(), a.cout);
-    int rp_taps[9];
-    if (rowpair_eligible(ctx, a, rp_taps)) return make_rowpair_op(ctx, pl, a, rp_taps);
+    int rs_taps[21];
+    const int rs_shape = rowstack_eligible(ctx, a, rs_taps);
+    if (rs_shape >= 0) return make_rowstack_op(ctx, pl, a, rs_shape, rs_taps);
     PatchGeom geom;
     if (patch_eligible(ctx, a, &geom)) return make_patch_op(ctx, pl, a, geom);
     Op op;
@@ -1191,7 +1197,7 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
             // TMA store of the same staged tile), read through the overlapping-window map with the 3 horizontal taps
             // folded into K.
             Op& prev = pl->ops.back();
-            if (!prev.patch || prev.head) return fail(W2L_ESTATE, "folded stride-2 block needs the patch kernel on the first block");
+            if ((!prev.patch && !prev.rowstack) || prev.head) return fail(W2L_ESTATE, "folded stride-2 block needs the patch kernel on the first block");
             const Layer& L1 = g.layers[g.face_enc[1][0]];
             Act e0;
             CKR(plan_input_act(pl, &e0, N, 96, 96, L1.cin, nw.layers[g.face_enc[1][0]], L1));
@@ -1199,12 +1205,13 @@ static int build_generator_plan(w2l_ctx* ctx, Plan* pl) {
             const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
             cuuint64_t od[4] = {16, 96, 96, (cuuint64_t)N};
             cuuint64_t os[3] = {(cuuint64_t)e0.Cs * 2, (cuuint64_t)e0.Wp * e0.Cs * 2, (cuuint64_t)96 * e0.Wp * e0.Cs * 2};
-            cuuint32_t ob[4] = {16, (cuuint32_t)kPatchTileW, (cuuint32_t)kPatchTileH, 1};
+            cuuint32_t ob[4] = {16, (cuuint32_t)kPatchTileW, (cuuint32_t)(prev.rowstack ? RsCfg1::kTileH : kPatchTileH), 1};
             cuuint32_t oe[4] = {1, 1, 1, 1};
-            CUresult r = enc(&prev.pp.tmO2, dt, 4, e0.base + (size_t)e0.x_off * e0.Cs, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CUresult r = enc(prev.rowstack ? &prev.rs.tmO2 : &prev.pp.tmO2, dt, 4, e0.base + (size_t)e0.x_off * e0.Cs, od, os, ob, oe, CU_TENSOR_MAP_INTERLEAVE_NONE,
                              CU_TENSOR_MAP_SWIZZLE_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
             if (r != CUDA_SUCCESS) return fail(W2L_ECUDA, "cuTensorMapEncodeTiled(dense copy) failed with %d", (int)r);
             prev.pp.has_out2 = 1;
+            prev.rs.has_out2 = 1;
             x = e0;
         }
     }
@@ -1346,8 +1353,8 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
             }
             case OP_CONV: {
                 if (op.head) {
-                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.pp.ep.head_out = op.cp.ep.head_out; op.rp.ep.head_out = op.cp.ep.head_out;
-                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.pp.ep.head_out_u8 = op.cp.ep.head_out_u8; op.rp.ep.head_out_u8 = op.cp.ep.head_out_u8;
+                    op.cp.ep.head_out = u8 ? nullptr : (float*)out0; op.pp.ep.head_out = op.cp.ep.head_out; op.rs.ep.head_out = op.cp.ep.head_out;
+                    op.cp.ep.head_out_u8 = u8 ? (unsigned char*)out0 : nullptr; op.pp.ep.head_out_u8 = op.cp.ep.head_out_u8; op.rs.ep.head_out_u8 = op.cp.ep.head_out_u8;
                 }
                 CKR(launch_conv(ctx, op, st));
                 break;
@@ -1539,12 +1546,10 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_tma_epi = !(e6 && e6[0] == '1');
         const char* e5 = getenv("W2L_DISABLE_MT2");
         ctx->use_mt2 = !(e5 && e5[0] == '1');
-        const char* e9 = getenv("W2L_DISABLE_ROWPAIR");
-        ctx->use_rowpair = !(e9 && e9[0] == '1');
+        const char* e9 = getenv("W2L_DISABLE_ROWSTACK");
+        ctx->use_rowstack = !(e9 && e9[0] == '1');
         const char* e11 = getenv("W2L_DISABLE_PDL");
         ctx->use_pdl = !(e11 && e11[0] == '1');
-        const char* e10 = getenv("W2L_ROWPAIR64");
-        ctx->use_rowpair64 = (e10 && e10[0] == '1');
         const char* e8 = getenv("W2L_DISABLE_SIDESTREAM");
         ctx->use_side = !(e8 && e8[0] == '1');
         const char* e4 = getenv("W2L_DISABLE_CTFUSED");
