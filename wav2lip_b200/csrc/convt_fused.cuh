@@ -10,9 +10,12 @@
 //   * a K step = one chunk of BK input channels: ONE TMA load of the (9 x 17 pixel) input patch chunk (the +1
 //     halo on the right/bottom is zero-filled at the border) and ONE 3-D TMA load of the 9 weight slabs
 //     [tap][64][BK] of that chunk;
-//   * the 9 taps of a K step are 9 shifted views of the patch (see conv_patch.cuh) feeding FOUR TMEM accumulators
-//     (one per output phase, 64 columns each) — consecutive MMAs hit different accumulators, which also hides the
-//     dependent-issue latency of tcgen05.mma;
+//   * the four output phases live side by side in ONE 256-column accumulator, in the order [00 | 01 | 11 | 10], and the
+//     9 taps are issued as 4 wide instructions, one per input shift (dy,dx) — an input pixel feeds every phase it
+//     touches at once:   (0,0) -> all four phases, N = 256;   (0,1) -> phases 01,11, N = 128 at column 64;
+//     (1,0) -> phases 11,10, N = 128 at column 128;   (1,1) -> phase 11, N = 64 at column 128.
+//     With the weight slabs packed in that order every B operand is a contiguous window.  An M=128 instruction costs
+//     >= 64 cycles whatever N is (A-operand path), so 4 instructions of 128+64+64+64 cycles replace 9 x 64;
 //   * two TMEM stages (2 x 4 x 64 = 512 columns) overlap the epilogue with the next unit's main loop;
 //   * two epilogue warp groups each drain two phases: scale/shift + ReLU, swizzled staging tile, one TMA tensor
 //     store per phase through a strided (every-other-pixel) view of the output channel slice.
@@ -36,8 +39,6 @@ struct alignas(64) ConvTParams {
     int stages;
     int patch_bytes, patch_stride;
     int act;
-    int tap_phase[9];    // accumulator (output phase py*2+px) of each tap
-    int tap_row[9];      // first patch row of each tap's view: dy*9 + dx
     float cscale[64], cshift[64];
 };
 
@@ -115,16 +116,12 @@ __global__ void __launch_bounds__(kCtThreads, 1) convt_fused_kernel(const __grid
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        constexpr uint32_t idesc = make_idesc<BN, kBF16>();
+        constexpr uint32_t idesc256 = make_idesc<4 * BN, kBF16>();
+        constexpr uint32_t idesc128 = make_idesc<2 * BN, kBF16>();
+        constexpr uint32_t idesc64 = make_idesc<BN, kBF16>();
         constexpr uint32_t kLayout = (BK == 64) ? 2u : (BK == 32) ? 4u : 6u;
-        constexpr uint32_t a_hi = ((static_cast<uint32_t>(kCtPW) * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29);
-        constexpr uint32_t b_hi = ((8u * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29);
-        uint32_t tap_off[9], tap_acc[9];
-#pragma unroll
-        for (int t = 0; t < 9; ++t) {
-            tap_off[t] = p.tap_row[t] * kRowBytes;
-            tap_acc[t] = p.tap_phase[t] * BN;
-        }
+        constexpr uint64_t a_hi = static_cast<uint64_t>(((static_cast<uint32_t>(kCtPW) * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29)) << 32;
+        constexpr uint64_t b_hi = static_cast<uint64_t>(((8u * kRowBytes) >> 4) | (1u << 14) | (kLayout << 29)) << 32;
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -134,25 +131,27 @@ __global__ void __launch_bounds__(kCtThreads, 1) convt_fused_kernel(const __grid
             mbar_wait(tempty_bar(ts), ts_phase ^ 1u);
             tc_fence_after();
             const uint32_t tmem_u = tmem_base + ts * (4 * BN);
-            uint32_t started = 0;  // bit ph set once accumulator ph has received its first MMA of this unit
             for (int c = 0; c < kc; ++c) {
                 mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
                 if (lane == 0) {
                     const uint32_t patch = smem_base + stage * stage_bytes;
                     const uint32_t wslab = patch + p.patch_stride;
+                    // input shifts (dy,dx) = patch rows dy*9 + dx; weight slabs in the packed order of w2l_api.cu
+                    const uint32_t a00 = ((patch + 0 * kRowBytes) >> 4) | 0x10000u;
+                    const uint32_t a01 = ((patch + 1 * kRowBytes) >> 4) | 0x10000u;
+                    const uint32_t a10 = ((patch + kCtPW * kRowBytes) >> 4) | 0x10000u;
+                    const uint32_t a11 = ((patch + (kCtPW + 1) * kRowBytes) >> 4) | 0x10000u;
+                    const uint32_t b0 = ((wslab + 0 * kSlab) >> 4) | 0x10000u;
+                    const uint32_t b4 = ((wslab + 4 * kSlab) >> 4) | 0x10000u;
+                    const uint32_t b6 = ((wslab + 6 * kSlab) >> 4) | 0x10000u;
+                    const uint32_t b8 = ((wslab + 8 * kSlab) >> 4) | 0x10000u;
 #pragma unroll
-                    for (int tap = 0; tap < 9; ++tap) {
-                        const uint32_t a_lo = ((patch + tap_off[tap]) >> 4) | 0x10000u;
-                        const uint32_t b_lo = ((wslab + tap * kSlab) >> 4) | 0x10000u;
-                        const uint32_t bit = 1u << p.tap_phase[tap];
-#pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            const uint32_t accum = (k != 0 || (started & bit)) ? 1u : 0u;
-                            tc_mma_f16(tmem_u + tap_acc[tap], (static_cast<uint64_t>(a_hi) << 32) | (a_lo + 2u * k),
-                                       (static_cast<uint64_t>(b_hi) << 32) | (b_lo + 2u * k), idesc, accum);
-                        }
-                        started |= bit;
+                    for (int k = 0; k < BK / 16; ++k) {
+                        tc_mma_f16(tmem_u, a_hi | (a00 + 2u * k), b_hi | (b0 + 2u * k), idesc256, (c | k) != 0 ? 1u : 0u);
+                        tc_mma_f16(tmem_u + BN, a_hi | (a01 + 2u * k), b_hi | (b4 + 2u * k), idesc128, 1u);
+                        tc_mma_f16(tmem_u + 2 * BN, a_hi | (a10 + 2u * k), b_hi | (b6 + 2u * k), idesc128, 1u);
+                        tc_mma_f16(tmem_u + 2 * BN, a_hi | (a11 + 2u * k), b_hi | (b8 + 2u * k), idesc64, 1u);
                     }
                     tc_commit(empty_bar(stage));
                     if (c == kc - 1) tc_commit(tfull_bar(ts));
@@ -181,7 +180,8 @@ __global__ void __launch_bounds__(kCtThreads, 1) convt_fused_kernel(const __grid
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 const int ph = grp * 2 + h;
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ts * (4 * BN) + ph * BN;
+                const int cb = ph == 2 ? 3 : ph == 3 ? 2 : ph;  // accumulator column order is [00 | 01 | 11 | 10]
+                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + ts * (4 * BN) + cb * BN;
                 uint32_t v[BN];
 #pragma unroll
                 for (int c0 = 0; c0 < BN; c0 += 16) tmem_ld16(taddr + c0, v + c0);

@@ -787,7 +787,7 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
 static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const LayerW& lw, const Act& in, const Act& out) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available");
-    const PackedW& w = lw.ph.back();  // all 9 taps, tap = r*3 + s
+    const PackedW& w = lw.ph.back();  // all 9 taps, grouped by input shift (load_layer)
     Op op;
     op.type = OP_CONV;
     op.name = L.name + " [fused 4-phase]";
@@ -829,13 +829,6 @@ static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const Lay
     if (t.stages < 2) return fail(W2L_EINVAL, "%s: fused convT does not fit shared memory", L.name.c_str());
     op.dyn_smem = t.stages * stage_bytes + fixed;
     t.act = ACT_RELU;
-    for (int r = 0; r < 3; ++r)
-        for (int s2 = 0; s2 < 3; ++s2) {
-            const int py = (r + 1) & 1, px = (s2 + 1) & 1;       // r == (py + pad) mod stride, pad = 1
-            const int dy = (py + 1 - r) / 2, dx = (px + 1 - s2) / 2;
-            t.tap_phase[r * 3 + s2] = py * 2 + px;
-            t.tap_row[r * 3 + s2] = dy * kCtPW + dx;
-        }
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(t.cscale, lw.scale, kCtBN * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(t.cshift, lw.shift, kCtBN * 4, cudaMemcpyDeviceToHost));
@@ -1045,11 +1038,15 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
                 lw->ph.push_back(pw);
             }
         if (!ctx->x2 && L.cout == kCtBN && L.kh == 3 && L.kw == 3 && L.sh == 2 && L.sw == 2 && L.ph == 1 && L.pw == 1 && L.out_pad == 1) {
-            // all nine taps in (r, s) order for the fused four-phase kernel
-            std::vector<std::pair<int, int>> rs;
+            // all nine taps for the fused four-phase kernel, grouped by the input shift (dy,dx) they read and, inside a
+            // group, in the accumulator's phase order [00 | 01 | 11 | 10] (convt_fused.cuh): tap (r,s) belongs to phase
+            // ((r+1)&1, (s+1)&1) and reads in[y + (r==0), x + (s==0)]
+            std::vector<std::pair<int, int>> rs = {{1, 1}, {1, 2}, {2, 2}, {2, 1},   // shift (0,0): phases 00 01 11 10
+                                                   {1, 0}, {2, 0},                   // shift (0,1): phases 01 11
+                                                   {0, 2}, {0, 1},                   // shift (1,0): phases 11 10
+                                                   {0, 0}};                          // shift (1,1): phase 11
             PackedW pw;
-            for (int r = 0; r < 3; ++r)
-                for (int s2 = 0; s2 < 3; ++s2) { rs.push_back({r, s2}); pw.dy.push_back(0); pw.dx.push_back(0); }
+            for (int t = 0; t < 9; ++t) { pw.dy.push_back(0); pw.dx.push_back(0); }
             CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, true, rs, pad_to, st));
             lw->ph.push_back(pw);
             lw->has_all_taps = true;
