@@ -1613,6 +1613,7 @@ int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* na
         if (nm.rfind("module.", 0) == 0) nm = nm.substr(7);  // DataParallel-era checkpoints, inference.py:174-175
         tm[nm] = TensorRef{(const float*)dev_ptrs[i], numels[i]};
     }
+    CK(cudaDeviceSynchronize());  // queued forwards (asynchronous host submissions included) still read the old weights
     drop_plans(ctx, net);
     NetW& nw = ctx->nets[net];
     nw.loaded = false;
