@@ -11,6 +11,9 @@ with torch.no_grad():
     g = Wav2Lip().cuda().eval()
     y = g(torch.rand(3, 1, 80, 16).cuda(), torch.rand(3, 6, 96, 96).cuda())
     y5 = g(torch.rand(2, 2, 1, 80, 16).cuda(), torch.rand(2, 6, 2, 96, 96).cuda())
+    y6 = g(torch.rand(6, 1, 80, 16).cuda(), torch.rand(6, 6, 96, 96).cuda())   # enough tiles for the row-stack kernels
+    ys = list(g.infer_stream(iter([(torch.rand(5, 1, 80, 16), torch.rand(5, 6, 96, 96)),
+                                   (torch.rand(2, 1, 80, 16), torch.randint(0, 256, (2, 96, 96, 3), dtype=torch.uint8))])))
     u = g.infer_u8(torch.rand(3, 1, 80, 16).cuda(), torch.randint(0, 256, (3, 96, 96, 3), dtype=torch.uint8).cuda())
     s = SyncNet_color().cuda().eval()
     a, v = s(torch.rand(3, 1, 80, 16).cuda(), torch.rand(3, 15, 48, 96).cuda())
