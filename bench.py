@@ -211,7 +211,13 @@ def measure_extra(dev):
                          "ms": dtp * 1e3, "crops_per_s": n / dtp, "h2d_bytes": int(faces.numel() + melh.numel() * 4),
                          "d2h_bytes": int(outh.numel()), "pipelined_equals_sync": bool(torch.equal(outh, outh2)),
                          "synchronous_call": {"api": "w2l_generator_forward_u8_host", "ms": dt * 1e3, "crops_per_s": n / dt}}
-        del g
+        # inference.py's own call shape: one 4-D batch of 128 crops (inference.py:259-263, --wav2lip_batch_size 128)
+        mel128 = (torch.rand((128, 1, 80, 16)) * 8 - 4).to(dev)
+        face128 = torch.rand((128, 6, 96, 96)).to(dev)
+        ms = timeit(lambda: g(mel128, face128), 20)
+        out["generator_n128"] = {"config": "Wav2Lip.forward 4-D N=128 (inference.py batch), device-resident", "ms": ms,
+                                 "crops_per_s": 128 / ms * 1e3}
+        del g, mel128, face128
         # the fp32-faithful precision mode (split fp16 operands, 3 MMAs per product) on the headline workload
         gx = Wav2Lip()
         gx.precision = _lib.PREC_F32X
