@@ -126,6 +126,25 @@ int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_host, const uin
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_dev,
                         float* audio_emb_dev, float* face_emb_dev, int B, void* stream);
 
+/* Scope row (a8) + evaluation loops (wav2lip_train.py:262-292, hq_wav2lip_train.py eval): the expert-discriminator
+ * call on generated frames, `get_sync_loss` (wav2lip_train.py:192-198) up to the embeddings:
+ *   g[:, :, :, H/2:]  ->  cat([g[:, :, i] for i in range(syncnet_T)], dim=1)  ->  syncnet(mel, .)
+ * with the slice and the channel stack done as addressing by the ingest kernel:
+ *   mel (B,1,80,16), frames (B,3,T,96,96) with T == 5 -> audio_emb (B,512), face_emb (B,512). */
+int w2l_syncnet_forward_frames(w2l_ctx* ctx, const float* mel_dev, const float* frames_dev, float* audio_emb_dev,
+                               float* face_emb_dev, int B, int T, void* stream);
+
+/* Replaces `cosine_loss(a, v, y)` (wav2lip_train.py:178-183, color_syncnet_train.py:133-138):
+ *   d = F.cosine_similarity(a, v) (eps 1e-8);  loss = nn.BCELoss()(d.unsqueeze(1), y)  (mean; log clamped at -100).
+ *   a, v (B,D) fp32; y (B) fp32 targets or NULL for all ones (get_sync_loss, :197); loss: 1 float on the device.
+ *   Forward value only (the evaluation loops); deterministic summation order. */
+int w2l_cosine_bce_loss(w2l_ctx* ctx, const float* a_dev, const float* v_dev, const float* y_dev, int B, int D,
+                        float* loss_dev, void* stream);
+
+/* Replaces `recon_loss = nn.L1Loss()` (wav2lip_train.py:191, :228, :281): loss = mean |x - y| over n fp32 elements
+ * (16-byte aligned pointers); loss: 1 float on the device.  HBM-bound: 8 bytes read per element pair. */
+int w2l_l1_loss(w2l_ctx* ctx, const float* x_dev, const float* y_dev, int64_t n, float* loss_dev, void* stream);
+
 /* Replaces `Wav2Lip_disc_qual.forward(face_sequences)` (wav2lip.py:176-184):
  *   frames (B,3,T,96,96) -> prob (B*T,1), rows t-major (row = t*B + b). */
 int w2l_disc_forward(w2l_ctx* ctx, const float* frames_dev, float* prob_dev, int B, int T, void* stream);

@@ -23,7 +23,7 @@ EXPORTS = [
     "w2l_create", "w2l_destroy", "w2l_load_weights",
     "w2l_generator_forward", "w2l_generator_forward_host", "w2l_generator_forward_u8", "w2l_generator_forward_u8_host",
     "w2l_generator_submit_host", "w2l_generator_submit_u8_host", "w2l_host_wait",
-    "w2l_syncnet_forward", "w2l_disc_forward",
+    "w2l_syncnet_forward", "w2l_syncnet_forward_frames", "w2l_cosine_bce_loss", "w2l_l1_loss", "w2l_disc_forward",
     "w2l_conv_block_forward", "w2l_debug_layer_output",
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
     "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
@@ -78,6 +78,9 @@ def get_lib() -> C.CDLL:
     lib.w2l_mel_chunks.argtypes = [vp, vp, i64, C.c_double, vp, i64, vp]
     lib.w2l_syncnet_forward.argtypes = [vp, vp, vp, vp, vp, i32, vp]
     lib.w2l_disc_forward.argtypes = [vp, vp, vp, i32, i32, vp]
+    lib.w2l_syncnet_forward_frames.argtypes = [vp, vp, vp, vp, vp, i32, i32, vp]
+    lib.w2l_cosine_bce_loss.argtypes = [vp, vp, vp, vp, i32, i32, vp, vp]
+    lib.w2l_l1_loss.argtypes = [vp, vp, vp, i64, vp, vp]
     lib.w2l_conv_block_forward.argtypes = [vp, C.POINTER(LayerInfo), vp, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.w2l_debug_layer_output.argtypes = [vp, i32, i32, vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), vp]
     lib.w2l_melspectrogram.argtypes = [vp, vp, i64, vp, vp]

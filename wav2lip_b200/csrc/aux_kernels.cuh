@@ -43,7 +43,13 @@ struct IngestParams {
     int y_off, Wsrc;       // source row offset / row pitch
     int lo_off;            // > 0: split-operand mode, also write lo = x - fp16(x) at channel + lo_off
     int Cpix;              // channels per pixel of the destination (= Cpad, or 2*Cpad with a lo plane)
+    int cgrp;              // > 0: destination channel c comes from source (group c / cgrp, channel c % cgrp):
+    long long sG;          //      offset (c / cgrp) * sG + (c % cgrp) * sC — frames stacked on channels, wav2lip_train.py:194
 };
+
+__device__ __forceinline__ long long src_off(const IngestParams& p, int c) {
+    return p.cgrp > 0 ? (long long)(c / p.cgrp) * p.sG + (long long)(c % p.cgrp) * p.sC : (long long)c * p.sC;
+}
 
 template <bool kBF16>
 __global__ void ingest_kernel(const IngestParams p) {
@@ -61,7 +67,7 @@ __global__ void ingest_kernel(const IngestParams p) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int c = c0 + j;
-                h[j] = (c < p.C) ? to16<kBF16>(__ldg(s + c * p.sC)) : (uint16_t)0;
+                h[j] = (c < p.C) ? to16<kBF16>(__ldg(s + src_off(p, c))) : (uint16_t)0;
             }
             uint4 o;
             o.x = h[0] | ((uint32_t)h[1] << 16);
@@ -74,7 +80,7 @@ __global__ void ingest_kernel(const IngestParams p) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int c = c0 + j;
-                    l[j] = (c < p.C) ? to16<kBF16>(__ldg(s + c * p.sC) - from16<kBF16>(h[j])) : (uint16_t)0;
+                    l[j] = (c < p.C) ? to16<kBF16>(__ldg(s + src_off(p, c)) - from16<kBF16>(h[j])) : (uint16_t)0;
                 }
                 uint4 q;
                 q.x = l[0] | ((uint32_t)l[1] << 16);
@@ -268,6 +274,78 @@ __global__ void disc_head_kernel(const uint16_t* x, const float* w, const float*
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) prob[row] = 1.0f / (1.0f + __expf(-(s + b[0])));
+}
+
+// ---- evaluation-loop losses (wav2lip_train.py:178-198, 262-292; color_syncnet_train.py:133-138) -------------------------
+// cosine_loss: d = F.cosine_similarity(a, v) (eps 1e-8), loss = nn.BCELoss()(d.unsqueeze(1), y) — mean over the batch,
+// log terms clamped at -100 as torch does.  One warp per row, per-row terms to `terms`, then a single block sums them in
+// a fixed order (deterministic).  y == nullptr means a vector of ones (get_sync_loss, wav2lip_train.py:197).
+__global__ void cosine_bce_terms_kernel(const float* a, const float* v, const float* y, float* terms, int B, int D) {
+    const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= B) return;
+    const float* ar = a + (long long)row * D;
+    const float* vr = v + (long long)row * D;
+    float saa = 0.0f, svv = 0.0f, sav = 0.0f;
+    for (int i = lane; i < D; i += 32) {
+        const float x = ar[i], z = vr[i];
+        saa = fmaf(x, x, saa); svv = fmaf(z, z, svv); sav = fmaf(x, z, sav);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        saa += __shfl_xor_sync(0xffffffffu, saa, o);
+        svv += __shfl_xor_sync(0xffffffffu, svv, o);
+        sav += __shfl_xor_sync(0xffffffffu, sav, o);
+    }
+    if (lane == 0) {
+        const float d = sav / (fmaxf(sqrtf(saa), 1e-8f) * fmaxf(sqrtf(svv), 1e-8f));
+        const float t = y ? y[row] : 1.0f;
+        const float l1 = fmaxf(logf(d), -100.0f), l0 = fmaxf(logf(1.0f - d), -100.0f);
+        terms[row] = -(t * l1 + (1.0f - t) * l0);
+    }
+}
+
+// out[0] = scale * sum(x[0..n)) in a fixed order (one block)
+__global__ void sum_scale_kernel(const float* x, float* out, int n, float scale) {
+    __shared__ float sh[32];
+    float s = 0.0f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) out[0] = s * scale;
+    }
+}
+
+// nn.L1Loss() partial sums: partial[block] = sum |x - y| over the block's grid-stride share (16-byte loads; HBM-bound:
+// 8 bytes read per element pair).  The tail (n % 4) is handled by block 0.
+__global__ void l1_partial_kernel(const float* x, const float* y, float* partial, long long n) {
+    __shared__ float sh[32];
+    const long long n4 = n >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    float s = 0.0f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 a = __ldg(x4 + i), b = __ldg(y4 + i);
+        s += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = (n4 << 2) + threadIdx.x; i < n; i += blockDim.x) s += fabsf(x[i] - y[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.0f;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (threadIdx.x == 0) partial[blockIdx.x] = s;
+    }
 }
 
 }  // namespace w2l

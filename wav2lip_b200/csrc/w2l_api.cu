@@ -206,6 +206,8 @@ struct w2l_ctx {
     bool use_side = true;            // W2L_DISABLE_SIDESTREAM=1
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     void* stage[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    float* scratch = nullptr;  // partial sums of the loss kernels
+    size_t scratch_bytes = 0;
     long long host_seq = 0;   // host-buffer submissions so far (staging slot = seq & 1)
     int host_inflight = 0;    // submitted and not yet retired by host_drain
     size_t stage_bytes[6] = {0, 0, 0, 0, 0, 0};
@@ -1125,6 +1127,7 @@ static void add_ingest(Plan* pl, const char* name, int src_id, const Act& dst, i
     ip.Wp = dst.pitch(); ip.x_off = dst.x_off;
     ip.lo_off = dst.lo_off;
     ip.sB = sB; ip.sC = sC; ip.sT = sT; ip.y_off = y_off; ip.Wsrc = Wsrc;
+    ip.cgrp = 0; ip.sG = 0;
     pl->ops.push_back(op);
 }
 
@@ -1240,7 +1243,15 @@ static int build_syncnet_plan(w2l_ctx* ctx, Plan* pl) {
     CKR(plan_act(pl, &fe, N, 1, 1, 512, true));
     CKR(plan_act(pl, &ae, N, 1, 1, 512, true));
     add_ingest(pl, "ingest.mel", 0, melIn, N, 1, 1280, 1280, 0, 0, 16);
-    add_ingest(pl, "ingest.face", 1, faceIn, N, 15, 15 * 4608, 4608, 0, 0, 96);
+    if (pl->T > 0) {
+        // face input = generated / ground-truth frames (B,3,T,96,96): lower half, the T frames stacked on channels
+        // (c' = 3 t + c) — wav2lip_train.py:193-194 as addressing
+        const int T = pl->T;
+        add_ingest(pl, "ingest.frames", 1, faceIn, N, 3 * T, (long long)3 * T * 9216, (long long)T * 9216, 0, 48, 96);
+        pl->ops.back().ip.cgrp = 3; pl->ops.back().ip.sG = 9216;
+    } else {
+        add_ingest(pl, "ingest.face", 1, faceIn, N, 15, 15 * 4608, 4608, 0, 0, 96);
+    }
     TmpPool tpf, tpa;
     CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.face_enc, faceIn, &tpf, &fe, nullptr));
     CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.audio_enc, melIn, &tpa, &ae, nullptr));
@@ -1584,6 +1595,7 @@ int w2l_destroy(w2l_ctx* ctx) {
     if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]); }
+    if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->mel_tw) cudaFree(ctx->mel_tw);
     if (ctx->mel_bvals) cudaFree(ctx->mel_bvals);
     if (ctx->mel_boff) cudaFree(ctx->mel_boff);
@@ -1777,6 +1789,56 @@ int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float
     Plan* pl;
     CKR(get_plan(ctx, W2L_NET_SYNCNET, B, 0, &pl));
     return run_plan(ctx, pl, mel, face, a_emb, v_emb, (cudaStream_t)stream);
+}
+
+int w2l_syncnet_forward_frames(w2l_ctx* ctx, const float* mel, const float* frames, float* a_emb, float* v_emb, int B, int T,
+                               void* stream) {
+    if (!ctx || !mel || !frames || !a_emb || !v_emb) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0) return fail(W2L_EINVAL, "bad batch %d", B);
+    if (T != 5) return fail(W2L_EINVAL, "SyncNet_color takes syncnet_T = 5 frames (15 channels), got T=%d", T);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_SYNCNET, B, T, &pl));
+    return run_plan(ctx, pl, mel, frames, a_emb, v_emb, (cudaStream_t)stream);
+}
+
+static int ensure_scratch(w2l_ctx* ctx, size_t bytes) {
+    if (ctx->scratch_bytes >= bytes) return W2L_OK;
+    CK(cudaDeviceSynchronize());
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    ctx->scratch = nullptr; ctx->scratch_bytes = 0;
+    void* p = nullptr;
+    CKR(dev_alloc(&p, bytes));
+    ctx->scratch = (float*)p; ctx->scratch_bytes = bytes;
+    return W2L_OK;
+}
+
+int w2l_cosine_bce_loss(w2l_ctx* ctx, const float* a_emb, const float* v_emb, const float* y, int B, int D, float* loss, void* stream) {
+    if (!ctx || !a_emb || !v_emb || !loss) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || D <= 0) return fail(W2L_EINVAL, "bad shape B=%d D=%d", B, D);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CKR(ensure_scratch(ctx, (size_t)std::max(B, 4096) * 4));
+    cosine_bce_terms_kernel<<<(B + 3) / 4, 128, 0, st>>>(a_emb, v_emb, y, ctx->scratch, B, D);
+    sum_scale_kernel<<<1, 1024, 0, st>>>(ctx->scratch, loss, B, 1.0f / (float)B);
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int w2l_l1_loss(w2l_ctx* ctx, const float* x, const float* y, int64_t n, float* loss, void* stream) {
+    if (!ctx || !x || !y || !loss) return fail(W2L_EINVAL, "null argument");
+    if (n <= 0) return fail(W2L_EINVAL, "bad element count");
+    if ((((uintptr_t)x) | ((uintptr_t)y)) & 15) return fail(W2L_EINVAL, "inputs must be 16-byte aligned");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int blocks = (int)std::min<long long>(std::max<long long>((n / 4 + 255) / 256, 1), (long long)ctx->num_sms * 8);
+    CKR(ensure_scratch(ctx, (size_t)std::max(blocks, 4096) * 4));
+    l1_partial_kernel<<<blocks, 256, 0, st>>>(x, y, ctx->scratch, (long long)n);
+    sum_scale_kernel<<<1, 1024, 0, st>>>(ctx->scratch, loss, blocks, (float)(1.0 / (double)n));
+    ctx->launches += 2;
+    CK(cudaGetLastError());
+    return W2L_OK;
 }
 
 int w2l_disc_forward(w2l_ctx* ctx, const float* frames, float* prob, int B, int T, void* stream) {

@@ -29,3 +29,20 @@ class SyncNet_color(NativeNet):
         stream = torch.cuda.current_stream(face.device).cuda_stream
         _lib.check(ctx.lib.w2l_syncnet_forward(ctx.h, self._p(mel), self._p(face), self._p(a), self._p(v), B, C.c_void_p(stream)))
         return a, v
+
+    def forward_frames(self, audio_sequences, frames):
+        """The expert-discriminator call of `get_sync_loss` (wav2lip_train.py:192-196) on generator output / ground truth:
+        frames (B,3,T=5,96,96) -> lower half, T frames stacked on channels -> (audio_embedding, face_embedding).
+        Same result as forward(mel, cat([frames[:, :, i, 48:] for i in range(5)], 1)) without materialising the stack."""
+        ctx = self._ensure(frames)
+        mel, fr = self._in(audio_sequences), self._in(frames)
+        B = fr.shape[0]
+        if fr.dim() != 5 or tuple(fr.shape[1:]) != (3, 5, 96, 96) or tuple(mel.shape) != (B, 1, 80, 16):
+            raise ValueError(f"expected (B,1,80,16) and (B,3,5,96,96), got {tuple(mel.shape)} and {tuple(fr.shape)}")
+        a = torch.empty((B, 512), device=fr.device, dtype=torch.float32)
+        v = torch.empty((B, 512), device=fr.device, dtype=torch.float32)
+        if B == 0:
+            return a, v
+        stream = torch.cuda.current_stream(fr.device).cuda_stream
+        _lib.check(ctx.lib.w2l_syncnet_forward_frames(ctx.h, self._p(mel), self._p(fr), self._p(a), self._p(v), B, 5, C.c_void_p(stream)))
+        return a, v
