@@ -1253,8 +1253,14 @@ static int build_syncnet_plan(w2l_ctx* ctx, Plan* pl) {
         add_ingest(pl, "ingest.face", 1, faceIn, N, 15, 15 * 4608, 4608, 0, 0, 96);
     }
     TmpPool tpf, tpa;
-    CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.face_enc, faceIn, &tpf, &fe, nullptr));
+    // the two encoders are independent until the embeddings: the audio one (short launches, issued first) runs on the
+    // side stream while the face encoder runs on the main one
     CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.audio_enc, melIn, &tpa, &ae, nullptr));
+    pl->ops[0].lane = 1;  // ingest.mel
+    for (size_t i = 2; i < pl->ops.size(); ++i) pl->ops[i].lane = 1;
+    pl->has_side = true;
+    CKR(emit_chain(ctx, pl, W2L_NET_SYNCNET, s.layers, s.face_enc, faceIn, &tpf, &fe, nullptr));
+    const size_t join_at = pl->ops.size();
     for (int which = 0; which < 2; ++which) {
         Op op;
         op.type = OP_L2NORM;
@@ -1263,6 +1269,7 @@ static int build_syncnet_plan(w2l_ctx* ctx, Plan* pl) {
         op.aux_rows = N; op.aux_dim = 512; op.aux_out = which;
         pl->ops.push_back(op);
     }
+    pl->ops[join_at].join_side = true;
     return W2L_OK;
 }
 
