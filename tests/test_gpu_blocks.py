@@ -47,6 +47,7 @@ CASES = [
     ("sync 46x47 s2 -> 23x24", "c", 64, 128, 3, 2, 1, 0, False, 2, 46, 47),
     ("sync 23x24 res", "c", 128, 128, 3, 1, 1, 0, True, 2, 23, 24),
     ("disc 7x7 3->32 lrelu", "n", 3, 32, 7, 1, 3, 0, False, 2, 48, 96),
+    ("disc 7x7 3->32 lrelu N=9 (row-stack kernel)", "n", 3, 32, 7, 1, 3, 0, False, 9, 48, 96),
     ("disc k5 s(1,2)", "n", 32, 64, 5, (1, 2), 2, 0, False, 2, 48, 96),
     ("disc k5", "n", 64, 64, 5, 1, 2, 0, False, 2, 48, 48),
     ("disc k5 s2", "n", 128, 256, 5, 2, 2, 0, False, 2, 24, 24),

@@ -322,9 +322,20 @@ static RsKernelEntry g_rs_kernels[] = {
     {0, true, conv_rowstack_kernel<32, 2, 3, 3, 16, true, true>, false},
     {1, false, conv_rowstack_kernel<16, 3, 7, 1, 0, false, false>, false},
     {1, true, conv_rowstack_kernel<16, 3, 7, 1, 0, true, false>, false},
+    {2, false, conv_rowstack_kernel<32, 3, 7, 1, 0, false, false>, false},
+    {2, true, conv_rowstack_kernel<32, 3, 7, 1, 0, true, false>, false},
 };
-using RsCfg0 = RowStackCfg<32, 2, 3, 3, 16>;
-using RsCfg1 = RowStackCfg<16, 3, 7, 1, 0>;
+using RsCfg0 = RowStackCfg<32, 2, 3, 3, 16>;   // generator output block (+ head)
+using RsCfg1 = RowStackCfg<16, 3, 7, 1, 0>;    // generator first block (6 -> 16, 7x7 folded)
+using RsCfg2 = RowStackCfg<32, 3, 7, 1, 0>;    // disc first block (3 -> 32, 7x7 folded, LeakyReLU)
+struct RsShape { int PW, PH, tile_h, R, ndx, fixed, per_stage; };
+static RsShape rs_shape(int shape) {
+    switch (shape) {
+        case 0: return {RsCfg0::PW, RsCfg0::PH, RsCfg0::kTileH, 1, 3, RsCfg0::smem_bytes(0, true), RsCfg0::kStageStride};
+        case 1: return {RsCfg1::PW, RsCfg1::PH, RsCfg1::kTileH, 3, 1, RsCfg1::smem_bytes(0, false), RsCfg1::kStageStride};
+        default: return {RsCfg2::PW, RsCfg2::PH, RsCfg2::kTileH, 3, 1, RsCfg2::smem_bytes(0, false), RsCfg2::kStageStride};
+    }
+}
 
 typedef void (*CtKernelFn)(const ConvTParams);
 struct CtKernelEntry { int BK; bool bf16; CtKernelFn fn; bool attr_set; };
@@ -614,11 +625,13 @@ static int rowstack_eligible(const w2l_ctx* ctx, const ConvArgs& a, int* tap_of)
     int shape = -1;
     if (a.head && a.cout == 32 && w.cin_pad == 80 && w.cout_pad == 32 && w.ntaps == 9 && !w.fold && !a.in.nwin && a.in.wstride == 1) shape = 0;
     if (!a.head && a.cout == 16 && w.cout_pad == 16 && w.fold && w.ntaps == 7 && w.cin_pad == 64 && a.in.wstride == 1) shape = 1;
+    if (!a.head && a.cout == 32 && w.cout_pad == 32 && w.fold && w.ntaps == 7 && w.cin_pad == 64 && a.in.wstride == 1) shape = 2;
     if (shape < 0) return -1;
-    const int tile_h = shape == 0 ? RsCfg0::kTileH : RsCfg1::kTileH;
-    const int R = shape == 0 ? 1 : 3, ndx = shape == 0 ? 3 : 1, ty = 2 * R + 1;
+    const RsShape sh = rs_shape(shape);
+    const int tile_h = sh.tile_h, R = sh.R, ndx = sh.ndx, ty = 2 * R + 1;
     if (a.Wl % kRsTileW != 0 || a.Hl % tile_h != 0) return -1;   // 96 x 96 here; ragged tiles would waste the pipe
-    if ((long long)(a.Wl / kRsTileW) * (a.Hl / tile_h) * a.in.N < ctx->num_sms / 2) return -1;
+    // no batch-size threshold: the kernel choice (and with it the fp32 summation order) must not depend on N, so that a
+    // crop's result is bit-identical whatever batch it travels in (tests/test_gpu_nets.py)
     for (int i = 0; i < ndx * ty; ++i) tap_of[i] = -1;
     for (int t = 0; t < w.ntaps; ++t) {
         const int dx = w.dx[t], dy = w.dy[t];
@@ -633,6 +646,7 @@ static int make_rowstack_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, int shape
     Op op;
     op.type = OP_CONV;
     op.name = a.name + (shape == 0 ? " [rowstack x2]" : " [fold+rowstack x3]");
+    const RsShape sh = rs_shape(shape);
     op.rowstack = true;
     op.rs_shape = shape;
     op.head = a.head;
@@ -641,8 +655,7 @@ static int make_rowstack_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, int shape
     op.BN = C; op.BK = 64;
     RowStackParams& h = op.rs;
     memset(&h, 0, sizeof(h));
-    const int PW = shape == 0 ? RsCfg0::PW : RsCfg1::PW, PH = shape == 0 ? RsCfg0::PH : RsCfg1::PH;
-    const int tile_h = shape == 0 ? RsCfg0::kTileH : RsCfg1::kTileH;
+    const int PW = sh.PW, PH = sh.PH, tile_h = sh.tile_h;
     CKR(encode_act_map(ctx, &h.tmA0, a.in, 64, PW, PH, 1, 1, 1, a.name.c_str()));
     CKR(encode_w_map(ctx, &h.tmB0, w, 64, C, a.name.c_str()));
     if (shape == 0) {
@@ -654,10 +667,9 @@ static int make_rowstack_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a, int shape
     h.tiles_x = a.Wl / kRsTileW;
     h.tiles_y = a.Hl / tile_h;
     h.ox = shape == 0 ? -1 : 0;   // folded inputs: the window already starts at the leftmost tap
-    h.oy = shape == 0 ? -1 : -3;
-    for (int i = 0; i < (shape == 0 ? 9 : 7); ++i) h.tap_of[i] = tap_of[i];
-    const int fixed = shape == 0 ? RsCfg0::smem_bytes(0, true) : RsCfg1::smem_bytes(0, false);
-    const int per_stage = shape == 0 ? RsCfg0::kStageStride : RsCfg1::kStageStride;
+    h.oy = -sh.R;
+    for (int i = 0; i < sh.ndx * (2 * sh.R + 1); ++i) h.tap_of[i] = tap_of[i];
+    const int fixed = sh.fixed, per_stage = sh.per_stage;
     h.stages = std::min(kRsMaxStages, (kSmemBudget + kSmemExtra - fixed) / per_stage);
     op.dyn_smem = fixed + h.stages * per_stage;
     if (h.stages < 2) return fail(W2L_EINVAL, "%s: row-stack kernel smem plan %d B / %d stages", a.name.c_str(), op.dyn_smem, h.stages);
