@@ -6,6 +6,12 @@ import (wav2lip_train.py, color_syncnet_train.py), so they cannot be imported; t
   cosine_loss      /root/reference/wav2lip_train.py:178-183  (same text in color_syncnet_train.py:133-138, hq_wav2lip_train.py)
   recon_loss       /root/reference/wav2lip_train.py:191
   get_sync_loss    /root/reference/wav2lip_train.py:192-198  (syncnet_T = 5, hparams.py)
+
+Mode of the expert: wav2lip_train.py:187-189 / hq_wav2lip_train.py:189-191 construct the expert SyncNet, freeze its
+parameters and never call .eval() on it, so in the scripts its BatchNorm layers run on BATCH statistics (and keep
+updating their running averages) even inside eval_model.  This restatement — like the product — evaluates the expert in
+eval mode (running statistics), i.e. what the same function computes once the caller has put the expert in eval mode;
+batch-statistics BatchNorm belongs to the training row and is not built.
 """
 import torch
 from torch import nn

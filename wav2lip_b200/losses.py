@@ -65,6 +65,9 @@ def recon_loss(g, gt):
 
 
 def get_sync_loss(syncnet, mel, g):
-    """syncnet: a wav2lip_b200.models.SyncNet_color in eval mode; mel (B,1,80,16); g (B,3,5,96,96)."""
+    """syncnet: a wav2lip_b200.models.SyncNet_color in eval mode; mel (B,1,80,16); g (B,3,5,96,96).
+    Note: the reference scripts never call .eval() on their expert (wav2lip_train.py:187-189), so there its BatchNorm
+    uses batch statistics; here the expert runs on its running statistics (eval mode) — batch-statistics BatchNorm is
+    part of the training row that is not built."""
     a, v = syncnet.forward_frames(mel, g)
     return cosine_loss(a, v, None)
