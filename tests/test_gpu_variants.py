@@ -163,3 +163,19 @@ def test_launch_counter_and_profile():
     total_flop = sum(f for _, _, f in prof)
     assert abs(total_flop / (2 * 2 * 3966984192) - 1) < 0.001  # = 2 crops x 7.934 GFLOP minus the fused 1x1 head
     assert ctx.device_bytes() > 70e6   # >= the packed 16-bit weights (36.3 M params)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_two_devices_in_one_process():
+    """One context per device in the same process (kernel attributes are per device): same inputs, same bits."""
+    from wav2lip_b200.models import Wav2Lip
+    sd = O.make_state_dict("generator", 0)
+    mel, face = O.make_generator_inputs(5, seed=3)
+    outs = []
+    for dev in ("cuda:0", "cuda:1"):
+        g = Wav2Lip()
+        g.load_state_dict(sd, strict=True)
+        g = g.to(dev).eval()
+        with torch.no_grad():
+            outs.append(g(mel.to(dev), face.to(dev)).cpu())
+    assert torch.equal(outs[0], outs[1])
