@@ -257,7 +257,9 @@ def make_disc_inputs(b: int, t: int = 5, seed: int = 0):
 # --------------------------------------------------------------------------------------
 # The interpreter
 # --------------------------------------------------------------------------------------
-def block_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, row: Row) -> torch.Tensor:
+def block_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, row: Row, training: bool = False) -> torch.Tensor:
+    """One conv.py block.  training=True: BatchNorm on batch statistics, running stats in `sd` updated in place
+    (momentum 0.1, unbiased variance) exactly as nn.BatchNorm2d does in train mode."""
     kind, _cin, _cout, _k, s, p, op, res = row
     w = sd[f"{prefix}.conv_block.0.weight"]
     b = sd[f"{prefix}.conv_block.0.bias"]
@@ -273,7 +275,7 @@ def block_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, row
         sd[f"{prefix}.conv_block.1.running_var"],
         sd[f"{prefix}.conv_block.1.weight"],
         sd[f"{prefix}.conv_block.1.bias"],
-        training=False, momentum=0.1, eps=BN_EPS,
+        training=training, momentum=0.1, eps=BN_EPS,
     )
     if res:  # conv.py:16-18: added after BN, before ReLU
         y = y + x
@@ -281,7 +283,7 @@ def block_forward(x: torch.Tensor, sd: Dict[str, torch.Tensor], prefix: str, row
 
 
 def generator_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] = None,
-                      return_logits: bool = False):
+                      return_logits: bool = False, training: bool = False):
     """Wav2Lip.forward — wav2lip.py:87-125.  `taps`, if given, receives every block output."""
     five_d = face.dim() > 4
     B = audio.size(0)
@@ -291,7 +293,7 @@ def generator_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] =
 
     a = audio
     for i, row in enumerate(GEN_AUDIO_ENCODER):
-        a = block_forward(a, sd, f"audio_encoder.{i}", row)
+        a = block_forward(a, sd, f"audio_encoder.{i}", row, training)
         if taps is not None:
             taps[f"audio_encoder.{i}"] = a
 
@@ -299,7 +301,7 @@ def generator_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] =
     x = face
     for i, blk in enumerate(GEN_FACE_ENCODER):
         for j, row in enumerate(blk):
-            x = block_forward(x, sd, f"face_encoder_blocks.{i}.{j}", row)
+            x = block_forward(x, sd, f"face_encoder_blocks.{i}.{j}", row, training)
             if taps is not None:
                 taps[f"face_encoder_blocks.{i}.{j}"] = x
         feats.append(x)
@@ -307,12 +309,12 @@ def generator_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] =
     x = a
     for i, blk in enumerate(GEN_FACE_DECODER):
         for j, row in enumerate(blk):
-            x = block_forward(x, sd, f"face_decoder_blocks.{i}.{j}", row)
+            x = block_forward(x, sd, f"face_decoder_blocks.{i}.{j}", row, training)
             if taps is not None:
                 taps[f"face_decoder_blocks.{i}.{j}"] = x
         x = torch.cat((x, feats.pop()), dim=1)  # decoder channels first, wav2lip.py:108
 
-    x = block_forward(x, sd, "output_block.0", GEN_OUTPUT_BLOCK0)
+    x = block_forward(x, sd, "output_block.0", GEN_OUTPUT_BLOCK0, training)
     if taps is not None:
         taps["output_block.0"] = x
     logits = F.conv2d(x, sd["output_block.1.weight"], sd["output_block.1.bias"])
@@ -322,16 +324,16 @@ def generator_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] =
     return out
 
 
-def syncnet_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] = None):
+def syncnet_forward(sd, audio, face, taps: Optional[Dict[str, torch.Tensor]] = None, training: bool = False):
     """SyncNet_color.forward — syncnet.py:55-66.  Returns (audio_emb, face_emb)."""
     v = face
     for i, row in enumerate(SYNC_FACE_ENCODER):
-        v = block_forward(v, sd, f"face_encoder.{i}", row)
+        v = block_forward(v, sd, f"face_encoder.{i}", row, training)
         if taps is not None:
             taps[f"face_encoder.{i}"] = v
     a = audio
     for i, row in enumerate(SYNC_AUDIO_ENCODER):
-        a = block_forward(a, sd, f"audio_encoder.{i}", row)
+        a = block_forward(a, sd, f"audio_encoder.{i}", row, training)
         if taps is not None:
             taps[f"audio_encoder.{i}"] = a
     a = F.normalize(a.reshape(a.size(0), -1), p=2, dim=1)
