@@ -23,7 +23,7 @@ def round_mantissa10(t: torch.Tensor) -> torch.Tensor:
 def forward_with_rounding(sd, mel, face, round_ops: bool, fp16_store: bool):
     orig = O.block_forward
 
-    def patched(x, sd_, prefix, row):
+    def patched(x, sd_, prefix, row, training=False):
         kind = row[0]
         w = sd_[f"{prefix}.conv_block.0.weight"]
         sd2 = dict(sd_)
