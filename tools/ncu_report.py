@@ -3,6 +3,7 @@
   launches  <ncu --metrics gpu__time_duration.sum --csv log>            -> per-kernel time shares of the whole command
   step      <ncu --metrics dram__bytes_read.sum,... --csv log> <names>  -> per-step DRAM bytes / tensor-pipe % (JSON + table)
   full      <ncu -i rep --page raw --csv export> <names>                -> per-launch table of the --set full capture
+  table     <ncu --metrics ... --csv log>                               -> per-launch table without layer names
 
 <names> is a bench.py --profile-out file: its launch order is the order of the conv launches of one step.
 """
@@ -87,6 +88,19 @@ def step(path, names_path, command=""):
     print("# JSON " + json.dumps(js))
 
 
+def table(path):
+    """Per-launch table of an ncu --metrics CSV log (no layer names): kernel, time, tensor pipe %, DRAM MB, achieved GB/s."""
+    ls = _by_id(_rows(path))
+    print("# kernel | time us | tensor pipe % | dram read MB | dram write MB | DRAM GB/s | dram throughput % of peak")
+    for e in ls:
+        r = _scale(*e["dram__bytes_read.sum"], "byte")
+        w = _scale(*e["dram__bytes_write.sum"], "byte")
+        us = _scale(*e["gpu__time_duration.sum"], "us")
+        tp = e["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"][0]
+        dt = e.get("dram__throughput.avg.pct_of_peak_sustained_elapsed", (float("nan"), ""))[0]
+        print(f"{e['Kernel Name']} | {us:.1f} | {tp:.1f} | {r / 1e6:.2f} | {w / 1e6:.2f} | {(r + w) / us / 1e3:.0f} | {dt:.1f}")
+
+
 FULL_COLS = ["gpu__time_duration.sum", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
              "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
              "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -115,6 +129,8 @@ if __name__ == "__main__":
         launches(sys.argv[2])
     elif cmd == "step":
         step(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "")
+    elif cmd == "table":
+        table(sys.argv[2])
     elif cmd == "full":
         full(sys.argv[2], sys.argv[3])
     else:

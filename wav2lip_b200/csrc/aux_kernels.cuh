@@ -93,6 +93,48 @@ __global__ void ingest_kernel(const IngestParams p) {
     }
 }
 
+// Same conversion, four horizontally adjacent pixels per thread: one 16-byte load per source channel (the NCHW planes
+// are read with 4x the bytes in flight) and four 16-byte stores per 8 destination channels.  Needs W, the source row
+// pitch and all source strides to be multiples of 4 elements and a 16-byte aligned source (checked by the caller);
+// 16-bit modes only (no lo plane).
+template <bool kBF16>
+__global__ void ingest4_kernel(const IngestParams p) {
+    const int W4 = p.W >> 2;
+    const long long total = (long long)p.N * p.H * W4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W4) << 2;
+        const int y = (int)((i / W4) % p.H);
+        const int n = (int)(i / ((long long)W4 * p.H));
+        const int b = n % p.B, t = n / p.B;
+        const float* s = p.src + b * p.sB + t * p.sT + (long long)(y + p.y_off) * p.Wsrc + x;
+        uint16_t* d = p.dst + ((((long long)n * p.H + y) * p.Wp) + x + p.x_off) * p.Cpix;
+        for (int c0 = 0; c0 < p.Cpad; c0 += 8) {
+            float4 v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int c = c0 + j;
+                v[j] = (c < p.C) ? __ldg(reinterpret_cast<const float4*>(s + src_off(p, c))) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int px = 0; px < 4; ++px) {
+                uint16_t h[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float f = px == 0 ? v[j].x : px == 1 ? v[j].y : px == 2 ? v[j].z : v[j].w;
+                    h[j] = to16<kBF16>(f);
+                }
+                uint4 o;
+                o.x = h[0] | ((uint32_t)h[1] << 16);
+                o.y = h[2] | ((uint32_t)h[3] << 16);
+                o.z = h[4] | ((uint32_t)h[5] << 16);
+                o.w = h[6] | ((uint32_t)h[7] << 16);
+                *reinterpret_cast<uint4*>(d + (long long)px * p.Cpix + c0) = o;
+            }
+        }
+    }
+}
+
 // Batch assembly of inference.py:134-140 on the GPU: uint8 BGR crops (N,96,96,3) -> 6 channels
 // [crop with rows >= H/2 zeroed | crop] / 255 (float64 division rounded to float32, as np.concatenate(...)/255.
 // followed by torch.FloatTensor does), written in the first conv's input layout.
@@ -330,7 +372,17 @@ __global__ void l1_partial_kernel(const float* x, const float* y, float* partial
     const float4* x4 = reinterpret_cast<const float4*>(x);
     const float4* y4 = reinterpret_cast<const float4*>(y);
     float s = 0.0f;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < n4; i += 4 * stride) {  // four independent 16-byte load pairs in flight per thread
+        float4 a[4], b[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a[u] = __ldg(x4 + i + u * stride); b[u] = __ldg(y4 + i + u * stride); }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            s += fabsf(a[u].x - b[u].x) + fabsf(a[u].y - b[u].y) + fabsf(a[u].z - b[u].z) + fabsf(a[u].w - b[u].w);
+    }
+    for (; i < n4; i += stride) {
         const float4 a = __ldg(x4 + i), b = __ldg(y4 + i);
         s += fabsf(a.x - b.x) + fabsf(a.y - b.y) + fabsf(a.z - b.z) + fabsf(a.w - b.w);
     }

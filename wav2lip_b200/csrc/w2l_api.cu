@@ -1370,9 +1370,17 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
                 IngestParams ip = op.ip;
                 ip.src = (const float*)(op.ingest_src == 0 ? in0 : in1);
                 const long long total = (long long)ip.N * ip.H * ip.W;
-                const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
-                if (ctx->bf16) ingest_kernel<true><<<blocks, 256, 0, st>>>(ip);
-                else ingest_kernel<false><<<blocks, 256, 0, st>>>(ip);
+                const bool vec4 = ip.lo_off == 0 && ((ip.W | ip.Wsrc) & 3) == 0 && ((ip.sB | ip.sC | ip.sT | ip.sG) & 3) == 0 &&
+                                  (((uintptr_t)ip.src) & 15) == 0;
+                if (vec4) {
+                    const int blocks = (int)std::min<long long>((total / 4 + 255) / 256, ctx->num_sms * 16);
+                    if (ctx->bf16) ingest4_kernel<true><<<blocks, 256, 0, st>>>(ip);
+                    else ingest4_kernel<false><<<blocks, 256, 0, st>>>(ip);
+                } else {
+                    const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+                    if (ctx->bf16) ingest_kernel<true><<<blocks, 256, 0, st>>>(ip);
+                    else ingest_kernel<false><<<blocks, 256, 0, st>>>(ip);
+                }
                 ctx->launches++;
                 break;
             }
