@@ -15,6 +15,10 @@ with torch.no_grad():
             y = g(*ins[n])
             if n not in ref: ref[n] = y.clone()
             assert torch.equal(y, ref[n]), (it, n)
+        if it % 5 == 0:   # the asynchronous host pipeline with changing batch sizes (staging buffers grow, plans get evicted)
+            hb = [(ins[n][0].cpu(), ins[n][1].cpu()) for n in (7, 200, 33, 128)]
+            for (mel_c, face_c), yo in zip(hb, g.infer_stream(iter(hb))):
+                assert torch.equal(yo, ref[mel_c.shape[0]].cpu()), (it, mel_c.shape[0])
         a, v = s(ins[16][0], torch.rand(16, 15, 48, 96).cuda())
         p = d(torch.rand(4, 3, 5, 96, 96).cuda())
         assert torch.isfinite(a).all() and torch.isfinite(p).all()
