@@ -98,26 +98,18 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
     int r = init_mel_tables(ctx);
     if (r != W2L_OK) { delete ctx; return r; }
     {
-        const char* e1 = getenv("W2L_DISABLE_HALO");
-        const char* e2 = getenv("W2L_DISABLE_FOLD");
-        ctx->use_patch = !(e1 && e1[0] == '1');
-        ctx->use_fold = !(e2 && e2[0] == '1');
-        const char* e3 = getenv("W2L_DISABLE_BN256");
-        ctx->use_bn256 = !(e3 && e3[0] == '1');
-        const char* e7 = getenv("W2L_DISABLE_FOLDS2");
-        ctx->use_fold_s2 = !(e7 && e7[0] == '1');
-        const char* e6 = getenv("W2L_DISABLE_TMAEPI");
-        ctx->use_tma_epi = !(e6 && e6[0] == '1');
-        const char* e5 = getenv("W2L_DISABLE_MT2");
-        ctx->use_mt2 = !(e5 && e5[0] == '1');
-        const char* e9 = getenv("W2L_DISABLE_ROWSTACK");
-        ctx->use_rowstack = !(e9 && e9[0] == '1');
-        const char* e11 = getenv("W2L_DISABLE_PDL");
-        ctx->use_pdl = !(e11 && e11[0] == '1');
-        const char* e8 = getenv("W2L_DISABLE_SIDESTREAM");
-        ctx->use_side = !(e8 && e8[0] == '1');
-        const char* e4 = getenv("W2L_DISABLE_CTFUSED");
-        ctx->use_ctfused = !(e4 && e4[0] == '1');
+        // A/B switches, read once per context: W2L_DISABLE_<NAME>=1 turns one specialised path off (tests/test_gpu_variants.py)
+        auto enabled = [](const char* name) { const char* v = getenv(name); return !(v && v[0] == '1'); };
+        ctx->use_patch = enabled("W2L_DISABLE_HALO");
+        ctx->use_fold = enabled("W2L_DISABLE_FOLD");
+        ctx->use_fold_s2 = enabled("W2L_DISABLE_FOLDS2");
+        ctx->use_bn256 = enabled("W2L_DISABLE_BN256");
+        ctx->use_mt2 = enabled("W2L_DISABLE_MT2");
+        ctx->use_tma_epi = enabled("W2L_DISABLE_TMAEPI");
+        ctx->use_ctfused = enabled("W2L_DISABLE_CTFUSED");
+        ctx->use_rowstack = enabled("W2L_DISABLE_ROWSTACK");
+        ctx->use_side = enabled("W2L_DISABLE_SIDESTREAM");
+        ctx->use_pdl = enabled("W2L_DISABLE_PDL");
         if (ctx->x2) {  // the split-operand mode runs on the generic kernel with the direct epilogue only
             ctx->use_patch = ctx->use_fold = ctx->use_fold_s2 = ctx->use_ctfused = ctx->use_tma_epi = false;
         }
