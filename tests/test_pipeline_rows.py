@@ -79,3 +79,35 @@ def test_fused_u8_assembly_matches_reference_pipeline():
     assert np.array_equal(out_h, out)
     with pytest.raises(ValueError):
         g.infer_u8(torch.from_numpy(mel_b).cuda(), torch.zeros((N, 96, 96, 3), device="cuda"))
+
+
+@pytest.mark.gpu
+def test_inference_loop_end_to_end_matches_composed_oracle():
+    """examples/lipsync_loop.py (melspectrogram -> mel_chunks -> infer_stream over uint8 crops) against the oracle
+    composed the way inference.py:224-271 composes it: mel_oracle -> pipeline_oracle.mel_chunks -> assemble_batch ->
+    generator -> postprocess.  uint8 output through a float pipeline: <= 1 LSB."""
+    import importlib.util
+    import os
+    from wav2lip_b200.models import Wav2Lip
+    spec = importlib.util.spec_from_file_location(
+        "lipsync_loop", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "lipsync_loop.py"))
+    ex = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ex)
+    fps, batch = 25.0, 7                                   # 1.3 s of audio -> 33 frames -> batches 7,7,7,7,5
+    wav = M.make_wav(int(16000 * 1.3), seed=21, kind="mix")
+    rng = np.random.RandomState(5)
+    crops = rng.randint(0, 256, size=(10, 96, 96, 3), dtype=np.uint8)    # fewer crops than frames: looped
+    sd = O.make_state_dict("generator", 0, init="default")
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    got = ex.lipsync(g, wav, crops, fps, batch)
+    mels = P.mel_chunks(M.melspectrogram(wav), fps)
+    assert got.shape == (len(mels), 96, 96, 3) and got.dtype == np.uint8
+    idx = np.arange(len(mels)) % len(crops)
+    mel_b, img_b = P.assemble_batch(crops[idx], mels)
+    with torch.no_grad():
+        pred = O.generator_forward(sd, torch.from_numpy(mel_b), torch.from_numpy(img_b)).numpy()
+    ref = P.postprocess(pred)
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    assert d.max() <= 1 and (d == 0).mean() >= 0.98

@@ -69,14 +69,27 @@ class Wav2Lip(NativeNet):
         """Serving loop over HOST batches with the copies overlapped with the kernels (w2l_generator_submit_*_host /
         w2l_host_wait, include/w2l.h): `batches` yields (mel, faces) CPU tensors — fp32 (N,1,80,16) with either fp32
         (N,6,96,96) assembled inputs (inference.py:259-260) or uint8 (N,96,96,3) crops (inference.py:126) — and the
-        generator yields, in order, fp32 (N,3,96,96) or uint8 (N,96,96,3) CPU tensors.  Inputs are staged through pinned
-        buffers; batch k+1 is uploaded while batch k computes and batch k-1 downloads."""
+        generator yields, in order, fp32 (N,3,96,96) or uint8 (N,96,96,3) CPU tensors.  Inputs are staged through two
+        sets of pinned buffers that are reused from batch to batch; batch k+1 is uploaded while batch k computes and
+        batch k-1 downloads."""
         dev = torch.device(device if device is not None else next(self.parameters()).device)
         if dev.type != "cuda":
             raise RuntimeError("wav2lip_b200 has no CPU path: move the module to a CUDA device first")
         ctx = self._ensure(torch.empty(0, device=dev))
         lib = ctx.lib
-        pending = []   # (out tensor, keep-alive inputs)
+        pool = {}
+
+        def pinned(slot, kind, shape, dtype):
+            n = 1
+            for d in shape:
+                n *= int(d)
+            t = pool.get((slot, kind, dtype))
+            if t is None or t.numel() < n:
+                t = pool[(slot, kind, dtype)] = torch.empty(max(n, 1), dtype=dtype).pin_memory()
+            return t[:n].view(shape)
+
+        pending = []   # out buffers of the submissions in flight, oldest first
+        seq = 0
         try:
             for mel, faces in batches:
                 u8 = faces.dtype == torch.uint8
@@ -85,20 +98,24 @@ class Wav2Lip(NativeNet):
                     raise ValueError(f"bad batch shapes mel {tuple(mel.shape)} faces {tuple(faces.shape)}")
                 if N == 0:
                     raise ValueError("empty batch")
-                mel_p = mel.float().contiguous().pin_memory()
-                faces_p = faces.contiguous().pin_memory()
-                out = torch.empty((N, 96, 96, 3), dtype=torch.uint8).pin_memory() if u8 else torch.empty((N, 3, 96, 96)).pin_memory()
+                slot = seq & 1     # the batch that used this slot two submissions ago has been retired (and its output copied)
+                mel_p = pinned(slot, "mel", (N, 1, 80, 16), torch.float32)
+                mel_p.copy_(mel)
+                faces_p = pinned(slot, "faces", tuple(faces.shape), faces.dtype if u8 else torch.float32)
+                faces_p.copy_(faces)
+                out = pinned(slot, "out", (N, 96, 96, 3) if u8 else (N, 3, 96, 96), torch.uint8 if u8 else torch.float32)
                 if u8:
                     _lib.check(lib.w2l_generator_submit_u8_host(ctx.h, self._p(mel_p), self._p(faces_p), self._p(out), N))
                 else:
                     _lib.check(lib.w2l_generator_submit_host(ctx.h, self._p(mel_p), self._p(faces_p), self._p(out), N, 0))
-                pending.append((out, mel_p, faces_p))
+                pending.append(out)
+                seq += 1
                 if len(pending) == 2:
                     _lib.check(lib.w2l_host_wait(ctx.h, 1))
-                    yield pending.pop(0)[0]
+                    yield pending.pop(0).clone()
             while pending:
                 _lib.check(lib.w2l_host_wait(ctx.h, len(pending) - 1))
-                yield pending.pop(0)[0]
+                yield pending.pop(0).clone()
         finally:
             _lib.check(lib.w2l_host_wait(ctx.h, 0))
 
