@@ -5,7 +5,8 @@ only; /root/reference is not on the GPU box):
 
 The training scripts parse argv and touch the dataset on import, so the step is driven from here with their own
 statements (cited): wav2lip_train.py:178-198 (losses), :210-231 (the step), :357-360 (Adam over the generator's
-parameters, lr = hparams.initial_learning_rate = 1e-4) and color_syncnet_train.py:146-163.  The expert SyncNet is left in
+parameters, lr = hparams.initial_learning_rate = 1e-4), color_syncnet_train.py:146-163 and hq_wav2lip_train.py:213-255
+(generator + quality discriminator, Adam betas (0.5, 0.999)).  The expert SyncNet is left in
 its constructor's train mode, as the scripts leave it (wav2lip_train.py:187-189).
 
 Stored: loss values, per-parameter gradient fingerprints (sum, abs-sum, max-abs), a few raw gradient slices, the
@@ -24,7 +25,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, "/root/reference")
 
-from models import Wav2Lip, SyncNet_color  # noqa: E402  (the reference)
+from models import Wav2Lip, SyncNet_color, Wav2Lip_disc_qual  # noqa: E402  (the reference)
 from oracle import w2l_oracle as O  # noqa: E402
 
 syncnet_T = 5           # hparams.py
@@ -121,6 +122,51 @@ def main():
         sd = s.state_dict()
         out[f"sync{step}_sd_names"] = np.array(list(sd.keys()))
         out[f"sync{step}_sd_fp"] = np.stack([fp3(v) for v in sd.values()])
+
+    # ---------------- hq_wav2lip_train.py step ----------------
+    import torch.nn.functional as F
+    DISC_WT = 0.07                                                # hparams.disc_wt
+    model = Wav2Lip()
+    model.load_state_dict(O.make_state_dict("generator", 0, init="default"), strict=True)
+    disc = Wav2Lip_disc_qual()
+    disc.load_state_dict(O.make_state_dict("disc", 3, init="default"), strict=True)
+    syncnet = SyncNet_color()
+    syncnet.load_state_dict(O.make_state_dict("syncnet", 1, init="default"), strict=True)
+    for p in syncnet.parameters():
+        p.requires_grad = False
+    optimizer = optim.Adam([p for p in model.parameters() if p.requires_grad], lr=LR, betas=(0.5, 0.999))       # :418-419
+    disc_optimizer = optim.Adam([p for p in disc.parameters() if p.requires_grad], lr=LR, betas=(0.5, 0.999))   # :420-421
+    x, indiv_mels, mel, gt = train_inputs(B, seed=8)
+    for step in range(2):
+        disc.train(); model.train()                               # :213-214
+        optimizer.zero_grad(); disc_optimizer.zero_grad()         # :222-223
+        g = model(indiv_mels, x)                                  # :225
+        sync_loss = get_sync_loss(mel, g)                         # :228
+        # disc.perceptual_forward(g) (:233) moves its target with .cuda() (wav2lip.py:172) and cannot run on this CPU box;
+        # its arithmetic is forward() + BCE against ones (wav2lip.py:163-174 vs :176-184):
+        perceptual_loss = F.binary_cross_entropy(disc(g), torch.ones((g.size(0) * syncnet_T, 1)))
+        l1loss = recon_loss(g, gt)                                # :237
+        loss = SYNCNET_WT * sync_loss + DISC_WT * perceptual_loss + (1. - SYNCNET_WT - DISC_WT) * l1loss   # :239-240
+        loss.backward()                                           # :242
+        ggrads = {n: p.grad.detach().clone() for n, p in model.named_parameters()}
+        optimizer.step()                                          # :243
+        disc_optimizer.zero_grad()                                # :246
+        pred = disc(gt)                                           # :248
+        disc_real_loss = F.binary_cross_entropy(pred, torch.ones((len(pred), 1)))
+        disc_real_loss.backward()
+        pred = disc(g.detach())                                   # :252
+        disc_fake_loss = F.binary_cross_entropy(pred, torch.zeros((len(pred), 1)))
+        disc_fake_loss.backward()
+        dgrads = {n: p.grad.detach().clone() for n, p in disc.named_parameters()}
+        disc_optimizer.step()                                     # :255
+        out[f"hq{step}_losses"] = np.array([loss.item(), sync_loss.item(), perceptual_loss.item(), l1loss.item(),
+                                            disc_real_loss.item(), disc_fake_loss.item()])
+        out[f"hq{step}_gen_grad_names"] = np.array(list(ggrads.keys()))
+        out[f"hq{step}_gen_grad_fp"] = np.stack([fp3(v) for v in ggrads.values()])
+        out[f"hq{step}_disc_grad_names"] = np.array(list(dgrads.keys()))
+        out[f"hq{step}_disc_grad_fp"] = np.stack([fp3(v) for v in dgrads.values()])
+        out[f"hq{step}_gen_sd_fp"] = np.stack([fp3(v) for v in model.state_dict().values()])
+        out[f"hq{step}_disc_sd_fp"] = np.stack([fp3(v) for v in disc.state_dict().values()])
 
     np.savez_compressed(os.path.join(HERE, "train.npz"), **out)
     print("wrote train.npz:", {k: getattr(v, "shape", None) for k, v in out.items() if "names" not in k})

@@ -102,3 +102,29 @@ def test_syncnet_training_step_matches_reference(gold):
         assert sd_names == list(sd.keys())
         got_sd = np.stack([fp3(sd[n]) for n in sd_names])
         assert close(got_sd[:, 1], gold[f"sync{step}_sd_fp"][:, 1], 1e-5)
+
+
+def test_hq_training_step_matches_reference(gold):
+    """hq_wav2lip_train.py:213-255: generator step with sync + perceptual + L1, then the discriminator's real/fake step."""
+    torch.set_num_threads(os.cpu_count() or 1)
+    gen_sd = O.make_state_dict("generator", 0, init="default")
+    disc_sd = O.make_state_dict("disc", 3, init="default")
+    sync_sd = O.make_state_dict("syncnet", 1, init="default")
+    x, indiv_mels, mel, gt = _train_inputs(2, seed=8)
+    states = None
+    for step in range(2):
+        r = T.hq_train_step(gen_sd, disc_sd, sync_sd, x, indiv_mels, mel, gt, syncnet_wt=0.03, disc_wt=0.07, states=states)
+        states = r["states"]
+        losses = np.array([r[k].item() for k in ("loss", "sync_loss", "perceptual", "l1", "disc_real", "disc_fake")])
+        assert close(losses, gold[f"hq{step}_losses"], 2e-5), (step, losses, gold[f"hq{step}_losses"])
+        for who, grads in (("gen", r["gen_grads"]), ("disc", r["disc_grads"])):
+            names = list(gold[f"hq{step}_{who}_grad_names"])
+            assert names == list(grads.keys())
+            got = np.stack([fp3(grads[n]) for n in names])
+            ref = gold[f"hq{step}_{who}_grad_fp"]
+            assert close(got[:, 1], ref[:, 1], 2e-3), (who, np.abs(got[:, 1] / ref[:, 1] - 1).max())
+            assert close(got[:, 2], ref[:, 2], 2e-3)
+        got_sd = np.stack([fp3(v) for v in gen_sd.values()])
+        assert close(got_sd[:, 1], gold[f"hq{step}_gen_sd_fp"][:, 1], 1e-5)
+        got_dsd = np.stack([fp3(v) for v in disc_sd.values()])
+        assert close(got_dsd[:, 1], gold[f"hq{step}_disc_sd_fp"][:, 1], 1e-5)
