@@ -112,3 +112,85 @@ def block_backward(dy, x, w, gamma, row: Row, saved) -> dict:
     dw = conv_wgrad(x, dz, row)
     db = dz.sum(dim=(0, 2, 3))                                            # == 0 up to rounding when BatchNorm follows
     return {"dx": dx, "dw": dw, "db": db, "dgamma": dgamma, "dbeta": dbeta}
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Network level: the generator's training forward/backward as an explicit schedule of block calls — the op list the
+# round-2 training plan will replay (forward order, then the reverse with the skip-concat gradient split and the
+# residual gradient accumulation made explicit).  Checked against autograd in tests/test_backward_recipe.py.
+# ----------------------------------------------------------------------------------------------------------------------
+def _blk(sd, prefix):
+    return (sd[f"{prefix}.conv_block.0.weight"], sd[f"{prefix}.conv_block.0.bias"],
+            sd.get(f"{prefix}.conv_block.1.weight"), sd.get(f"{prefix}.conv_block.1.bias"))
+
+
+def generator_forward_backward(sd, audio, face, dloss_dout):
+    """Wav2Lip.forward in train mode (4-D call) followed by the full backward given dL/d(output).  Returns
+    (output, {parameter name: gradient}).  Only block_forward_train / block_backward and tensor slicing are used."""
+    from . import w2l_oracle as O
+    tape = []                                                  # (prefix, row, input, saved) in forward order
+
+    def run(x, prefix, row):
+        w, b, gamma, beta = _blk(sd, prefix)
+        y, saved = block_forward_train(x, w, b, gamma, beta, row)
+        tape.append((prefix, row, x, saved))
+        return y
+
+    a = audio
+    for i, row in enumerate(O.GEN_AUDIO_ENCODER):
+        a = run(a, f"audio_encoder.{i}", row)
+    feats = []
+    x = face
+    for i, blk in enumerate(O.GEN_FACE_ENCODER):
+        for j, row in enumerate(blk):
+            x = run(x, f"face_encoder_blocks.{i}.{j}", row)
+        feats.append(x)
+    x = a
+    cat_split = []                                             # channels of the decoder half of every concat
+    for i, blk in enumerate(O.GEN_FACE_DECODER):
+        for j, row in enumerate(blk):
+            x = run(x, f"face_decoder_blocks.{i}.{j}", row)
+        cat_split.append(x.shape[1])
+        x = torch.cat((x, feats[len(feats) - 1 - i]), dim=1)
+    x = run(x, "output_block.0", O.GEN_OUTPUT_BLOCK0)
+    hw, hb = sd["output_block.1.weight"], sd["output_block.1.bias"]
+    logits = F.conv2d(x, hw, hb)
+    out = torch.sigmoid(logits)
+
+    grads = {}
+    # head: sigmoid + 1x1 conv
+    dlog = dloss_dout * out * (1 - out)
+    grads["output_block.1.weight"] = torch.einsum("nohw,nchw->oc", dlog, x)[:, :, None, None]
+    grads["output_block.1.bias"] = dlog.sum(dim=(0, 2, 3))
+    dx = F.conv2d(dlog, hw.transpose(0, 1).contiguous())       # 1x1 dgrad
+
+    def back(dy):
+        prefix, row, xin, saved = tape.pop()
+        w, _b, gamma, _beta = _blk(sd, prefix)
+        g = block_backward(dy, xin, w, gamma, row, saved)
+        grads[f"{prefix}.conv_block.0.weight"] = g["dw"]
+        grads[f"{prefix}.conv_block.0.bias"] = g["db"]
+        if g["dgamma"] is not None:
+            grads[f"{prefix}.conv_block.1.weight"] = g["dgamma"]
+            grads[f"{prefix}.conv_block.1.bias"] = g["dbeta"]
+        return g["dx"]
+
+    dx = back(dx)                                              # output_block.0
+    dfeats = [None] * len(feats)
+    for i in reversed(range(len(O.GEN_FACE_DECODER))):
+        c = cat_split[i]
+        dfeats[len(feats) - 1 - i] = dx[:, c:]                 # the encoder-skip half of the concat (wav2lip.py:108)
+        dx = dx[:, :c]
+        for _ in O.GEN_FACE_DECODER[i]:
+            dx = back(dx)
+    da = dx                                                    # gradient of the audio embedding
+    dx = None
+    for i in reversed(range(len(O.GEN_FACE_ENCODER))):
+        d = dfeats[i] if dx is None else dx + dfeats[i]        # stage output feeds the next stage AND a skip connection
+        for _ in O.GEN_FACE_ENCODER[i]:
+            d = back(d)
+        dx = d
+    for _ in O.GEN_AUDIO_ENCODER:
+        da = back(da)
+    assert not tape
+    return out, grads
