@@ -21,6 +21,18 @@ import torch.nn.functional as F
 
 from .w2l_oracle import BN_EPS, Row, _pair
 
+# Precision model hook: every tensor-core operand (conv / dgrad / wgrad inputs) passes through Q before the contraction,
+# and stored activations through QS.  Identity by default; tests/test_precision_model.py sets bf16 rounding to size the
+# gradient-parity tolerances of the training kernels.
+Q = lambda t: t      # noqa: E731
+QS = lambda t: t     # noqa: E731
+
+
+def set_precision_model(q=None, qs=None):
+    global Q, QS
+    Q = q if q is not None else (lambda t: t)
+    QS = qs if qs is not None else (lambda t: t)
+
 
 def conv_dgrad(dz: torch.Tensor, w: torch.Tensor, row: Row, in_hw: Tuple[int, int]) -> torch.Tensor:
     kind, _cin, _cout, k, s, p, op, _res = row
@@ -28,22 +40,23 @@ def conv_dgrad(dz: torch.Tensor, w: torch.Tensor, row: Row, in_hw: Tuple[int, in
     H, W = in_hw
     if kind == "t":
         # transposed conv forward: z = convT(x, w (Cin,Cout,kh,kw)); its input gradient is a plain strided conv of dz
-        return F.conv2d(dz, w, None, stride=(sh, sw), padding=(ph, pw))
+        return F.conv2d(Q(dz), Q(w), None, stride=(sh, sw), padding=(ph, pw))
     if sh == 1 and sw == 1:
         w2 = w.flip(2, 3).transpose(0, 1).contiguous()                 # (Cin, Cout, kh, kw), taps flipped
-        return F.conv2d(dz, w2, None, stride=1, padding=(kh - 1 - ph, kw - 1 - pw))
+        return F.conv2d(Q(dz), Q(w2), None, stride=1, padding=(kh - 1 - ph, kw - 1 - pw))
     # strided conv: the transposed conv with the SAME weight tensor; output_padding recovers the rows/cols the forward
     # conv's floor division dropped
     Ho, Wo = dz.shape[2], dz.shape[3]
     oph = H - ((Ho - 1) * sh - 2 * ph + kh)
     opw = W - ((Wo - 1) * sw - 2 * pw + kw)
-    return F.conv_transpose2d(dz, w, None, stride=(sh, sw), padding=(ph, pw), output_padding=(oph, opw))
+    return F.conv_transpose2d(Q(dz), Q(w), None, stride=(sh, sw), padding=(ph, pw), output_padding=(oph, opw))
 
 
 def conv_wgrad(x: torch.Tensor, dz: torch.Tensor, row: Row) -> torch.Tensor:
     """Per-tap GEMMs with the pixel index as the contraction dimension (what the tcgen05 wgrad kernel will do)."""
     kind, cin, cout, k, s, p, op, _res = row
     (kh, kw), (sh, sw), (ph, pw) = _pair(k), _pair(s), _pair(p)
+    x, dz = Q(x), Q(dz)
     if kind == "t":
         # z[n,co, y*sh - ph + r, x*sw - pw + s] += x[n,ci,y,x] * w[ci,co,r,s]
         N, _, H, W = x.shape
@@ -73,12 +86,12 @@ def block_forward_train(x, w, b, gamma, beta, row: Row):
     """Forward of one block in train mode, returning what the backward needs (z_hat and invstd instead of z)."""
     kind, _cin, _cout, _k, s, p, op, res = row
     if kind == "t":
-        z = F.conv_transpose2d(x, w, b, stride=_pair(s), padding=_pair(p), output_padding=_pair(op))
+        z = F.conv_transpose2d(Q(x), Q(w), b, stride=_pair(s), padding=_pair(p), output_padding=_pair(op))
     else:
-        z = F.conv2d(x, w, b, stride=_pair(s), padding=_pair(p))
+        z = F.conv2d(Q(x), Q(w), b, stride=_pair(s), padding=_pair(p))
     if kind == "n":
-        y = F.leaky_relu(z, 0.01)
-        return y, {"z": z}
+        y = QS(F.leaky_relu(z, 0.01))
+        return y, {"z": QS(z)}
     mean = z.mean(dim=(0, 2, 3))
     var = z.var(dim=(0, 2, 3), unbiased=False)
     invstd = (var + BN_EPS).rsqrt()
@@ -86,8 +99,8 @@ def block_forward_train(x, w, b, gamma, beta, row: Row):
     u = zhat * gamma[None, :, None, None] + beta[None, :, None, None]
     if res:
         u = u + x
-    y = F.relu(u)
-    return y, {"zhat": zhat, "invstd": invstd, "y": y}
+    y = QS(F.relu(u))
+    return y, {"zhat": QS(zhat), "invstd": invstd, "y": y}
 
 
 def block_backward(dy, x, w, gamma, row: Row, saved) -> dict:
