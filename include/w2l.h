@@ -167,7 +167,9 @@ int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y_dev, int* 
 
 /* Replaces `audio.melspectrogram(wav)` (audio.py:45-51 with hparams.py:33-73):
  *   wav (L) fp32 -> mel (80, 1 + L/200) fp32 in [-4,4], row-major as numpy returns it.
- *   L must be > 400 (reflect padding), as librosa requires. */
+ *   L >= 2; clips shorter than n_fft/2 = 400 samples reflect more than once, as np.pad(mode="reflect") does.
+ *   w2l_melspectrogram_host first retires every asynchronous host submission of the context (w2l_host_wait(ctx, 0)):
+ *   it shares their staging buffers. */
 int w2l_melspectrogram(w2l_ctx* ctx, const float* wav_dev, int64_t n_samples, float* mel_dev, void* stream);
 int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_host, int64_t n_samples, float* mel_host);
 /* number of frames for n_samples: 1 + n_samples/200 (librosa center=True) */
@@ -185,6 +187,12 @@ int w2l_mel_chunks(w2l_ctx* ctx, const float* mel_dev, int64_t n_frames, double 
 int w2l_set_debug(w2l_ctx* ctx, int keep_all_layer_outputs);
 /* the kernel's own (80 x 401) Slaney mel filterbank, dense fp32, written to HOST memory */
 int w2l_mel_basis_host(float* out_host);
+
+/* Range guard of the fp16 modes (W2L_PREC_F16 / _F32X): every epilogue that stores an activation sets a sticky
+ * per-device flag when the rounded value leaves the fp16 range (|v| > 65504 -> inf, or NaN).  Synchronises `stream`,
+ * writes the flag to *flag (0 = every activation stored so far was finite) and, if `clear`, resets it.  A checkpoint
+ * that trips it must run in W2L_PREC_BF16 (fp32's exponent range).  bf16 contexts never set it. */
+int w2l_f16_overflow(w2l_ctx* ctx, int clear, int* flag, void* stream);
 
 /* ---- instrumentation ---- */
 /* kernels launched by this library since the context was created (all streams) */

@@ -68,8 +68,10 @@ def hann_periodic(n: int = WIN) -> np.ndarray:
 def stft(y: np.ndarray) -> np.ndarray:
     """librosa.stft(y, 800, 200, 800) -> complex64 (401, 1 + len(y)//200)."""
     y = np.asarray(y, dtype=np.float64)
-    if y.shape[0] < N_FFT // 2 + 1:
-        raise ValueError("reflect padding needs len(y) > n_fft//2")
+    if y.shape[0] < 2:
+        raise ValueError("reflect padding needs at least 2 samples")
+    # librosa 0.7.0 pads with np.pad(mode="reflect") and does not check the length: clips shorter than n_fft//2 are
+    # reflected more than once (np.pad's own rule), they do not raise
     yp = np.pad(y, N_FFT // 2, mode="reflect")
     n_frames = 1 + (yp.shape[0] - N_FFT) // HOP
     idx = np.arange(N_FFT)[:, None] + HOP * np.arange(n_frames)[None, :]

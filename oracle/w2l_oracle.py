@@ -19,7 +19,7 @@ trees and the product's C++ layer tables.  Pinning: tests/golden/make_golden.py 
 the REAL reference modules (imported from /root/reference in the build container)
 on seeded weights/inputs and commits their outputs under tests/golden/; the CPU test
 tests/test_oracle_golden.py checks this restatement against those vectors, and
-tests/test_oracle_vs_reference.py checks it against the live reference whenever
+tests/test_oracle_golden.py checks it against the live reference whenever
 /root/reference is present.
 
 State-dict keys are the reference's own (352 tensors for the generator), so a

@@ -283,3 +283,110 @@ def test_bf16_precision_mode_runs(golden_dir):
     with torch.no_grad():
         y = g(mel.cuda(), face.cuda()).cpu().numpy()
     assert np.abs(y - gold["gen4_default_out"]).max() <= BAR
+
+
+def test_bf16_mode_syncnet_and_disc_vs_reference_golden(golden_dir):
+    """BASELINE configs[3] names bf16 for SyncNet_color + Wav2Lip_disc_qual: the bf16-operand build of both nets against
+    the REAL reference's fp32 outputs.  bf16 carries 8 mantissa bits (fp16: 11), so the bar is the dtype's own:
+    unit-norm embeddings (entries <= 0.25) within 4e-3, disc probability within 4e-3 (measured ~1e-3 / ~1e-4)."""
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip_disc_qual
+    gs = np.load(os.path.join(golden_dir, "syncnet.npz"))
+    s = SyncNet_color()
+    s.precision = _lib.PREC_BF16
+    s.load_state_dict(O.make_state_dict("syncnet", 0), strict=True)
+    s = s.cuda().eval()
+    mel, face = O.make_syncnet_inputs(3, 0)
+    with torch.no_grad():
+        a, v = s(mel.cuda(), face.cuda())
+    a, v = a.cpu().numpy(), v.cpu().numpy()
+    assert np.abs(a - gs["sync_a"]).max() <= 4e-3, np.abs(a - gs["sync_a"]).max()
+    assert np.abs(v - gs["sync_v"]).max() <= 4e-3, np.abs(v - gs["sync_v"]).max()
+    np.testing.assert_allclose(np.linalg.norm(a, axis=1), 1.0, atol=1e-5)
+    cos_gpu, cos_ref = (a * v).sum(1), (gs["sync_a"] * gs["sync_v"]).sum(1)
+    assert np.abs(cos_gpu - cos_ref).max() <= 1e-2
+    gd = np.load(os.path.join(golden_dir, "disc.npz"))
+    d = Wav2Lip_disc_qual()
+    d.precision = _lib.PREC_BF16
+    d.load_state_dict(O.make_state_dict("disc", 0), strict=True)
+    d = d.cuda().eval()
+    with torch.no_grad():
+        p = d(O.make_disc_inputs(2, 5, 0).cuda())
+    assert np.abs(p.cpu().numpy() - gd["disc_out"]).max() <= 4e-3
+
+
+def test_generator_headline_shape_b128_t5_vs_oracle():
+    """The metric's own call — B=128, T=5, one 5-D batch of 640 crops — against the oracle on 8 sampled crops, logits
+    included (BASELINE weights: reference default-init statistics + randomised BatchNorm; bar 1e-3 on the output)."""
+    from wav2lip_b200.models import Wav2Lip
+    sd = O.make_state_dict("generator", 0, init="default")
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    B, T = 128, 5
+    mel, face = O.make_generator_inputs(B, seed=21, t=T)
+    with torch.no_grad():
+        y = g(mel.cuda(), face.cuda()).cpu()
+    assert tuple(y.shape) == (B, 3, T, 96, 96)
+    picks = [(0, 0), (127, 4), (64, 2), (5, 1), (99, 3), (31, 0), (77, 4), (126, 2)]
+    m4 = torch.stack([mel[b, t] for b, t in picks])
+    f4 = torch.stack([face[b, :, t] for b, t in picks])
+    with torch.no_grad():
+        ref = O.generator_forward(sd, m4, f4)
+    got = torch.stack([y[b, :, t] for b, t in picks])
+    err = (got - ref).abs().max().item()
+    assert err <= BAR, err
+    # logits: sigmoid is monotone, so compare in logit space where the output is not saturated
+    lg, lr = torch.logit(got.clamp(1e-6, 1 - 1e-6)), torch.logit(ref.clamp(1e-6, 1 - 1e-6))
+    assert (lg - lr).abs().max().item() <= 5e-3
+
+
+def test_fp16_range_guard_raises_instead_of_returning_inf():
+    """A checkpoint whose activations leave the fp16 range (|v| > 65504) must not return silently poisoned results:
+    the epilogues set a sticky device flag (w2l_f16_overflow), the mirror checks it after the first forward following
+    a weight load and raises, naming the bf16 mode — which runs the same weights finitely."""
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import Wav2Lip
+    sd = O.make_state_dict("generator", 0)
+    k = "face_encoder_blocks.0.0.conv_block.1.weight"   # BatchNorm gamma of the first block: scale its output by 1e6
+    sd = {n: (t.clone() * 1.0e6 if n == k else t.clone()) for n, t in sd.items()}
+    mel, face = O.make_generator_inputs(2, 0)
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().eval()
+    with torch.no_grad():
+        with pytest.raises(_lib.W2LError, match="fp16 range"):
+            g(mel.cuda(), face.cuda())
+    gb = Wav2Lip()
+    gb.precision = _lib.PREC_BF16
+    gb.load_state_dict(sd, strict=True)
+    gb = gb.cuda().eval()
+    with torch.no_grad():
+        y = gb(mel.cuda(), face.cuda())
+    assert torch.isfinite(y).all()
+    # sane weights do not trip the guard (and clear nothing they should not)
+    g2 = Wav2Lip()
+    g2.load_state_dict(O.make_state_dict("generator", 0), strict=True)
+    g2 = g2.cuda().eval()
+    with torch.no_grad():
+        g2(mel.cuda(), face.cuda())
+    assert not g2._w2l_ctx.f16_overflow(clear=False)
+
+
+def test_inputs_on_the_wrong_device_raise_cleanly(gen_stress):
+    """a CPU mel next to a CUDA face used to be dereferenced on the device (sticky illegal-address error)."""
+    from wav2lip_b200 import _lib, losses
+    from wav2lip_b200.models import SyncNet_color
+    mel, face = O.make_generator_inputs(2, 0)
+    with torch.no_grad():
+        with pytest.raises(_lib.W2LError):
+            gen_stress(mel, face.cuda())
+        with pytest.raises(_lib.W2LError):
+            gen_stress.infer_u8(mel, torch.zeros(2, 96, 96, 3, dtype=torch.uint8).cuda())
+        s = SyncNet_color().cuda().eval()
+        with pytest.raises(_lib.W2LError):
+            s(torch.zeros(2, 1, 80, 16), torch.zeros(2, 15, 48, 96).cuda())
+        with pytest.raises(_lib.W2LError):
+            losses.recon_loss(torch.zeros(8, 8).cuda(), torch.zeros(8, 8))
+        y = gen_stress(mel.cuda(), face.cuda())   # the process is still healthy
+    assert torch.isfinite(y).all()

@@ -53,10 +53,12 @@ def test_mel_edges():
     # silence hits the 1e-5 floor -> exactly -4.0 everywhere
     mel = M.melspectrogram(np.zeros(4000, dtype=np.float32))
     assert mel.shape == (80, 21) and np.all(mel == -4.0)
-    # shortest legal input for reflect padding
     assert M.melspectrogram(np.ones(401, dtype=np.float32)).shape == (80, 3)
+    # librosa 0.7.0 does not check the length: shorter clips are reflected more than once by np.pad
+    assert M.melspectrogram(np.ones(400, dtype=np.float32)).shape == (80, 3)
+    assert M.melspectrogram(np.ones(57, dtype=np.float32)).shape == (80, 1)
     with pytest.raises(ValueError):
-        M.melspectrogram(np.ones(400, dtype=np.float32))
+        M.melspectrogram(np.ones(1, dtype=np.float32))
     # preemphasis: zero initial state
     y = M.preemphasis(np.array([1.0, 1.0, 1.0], dtype=np.float32))
     np.testing.assert_allclose(y, [1.0, 0.03, 0.03], atol=1e-12)

@@ -27,6 +27,7 @@ EXPORTS = [
     "w2l_conv_block_forward", "w2l_debug_layer_output",
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
     "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
+    "w2l_f16_overflow",
 ]
 
 
@@ -93,6 +94,7 @@ def get_lib() -> C.CDLL:
     lib.w2l_device_bytes.argtypes = [vp]
     lib.w2l_device_bytes.restype = i64
     lib.w2l_profile_plan.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
+    lib.w2l_f16_overflow.argtypes = [vp, i32, C.POINTER(i32), vp]
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here == header / library mismatch
     if lib.w2l_abi_version() != 1:
@@ -149,6 +151,12 @@ class Context:
 
     def device_bytes(self) -> int:
         return int(self.lib.w2l_device_bytes(self.h))
+
+    def f16_overflow(self, clear: bool = True, stream: int = 0) -> bool:
+        """True if an fp16 epilogue stored an inf/NaN activation since the flag was last cleared (synchronises)."""
+        flag = C.c_int(0)
+        check(self.lib.w2l_f16_overflow(self.h, 1 if clear else 0, C.byref(flag), C.c_void_p(stream)))
+        return bool(flag.value)
 
     def set_debug(self, keep_all: bool):
         check(self.lib.w2l_set_debug(self.h, 1 if keep_all else 0))

@@ -5,8 +5,9 @@ a float32 (80, 1 + len(wav)//200) array in [-4, 4] out — and additionally acce
 (then returns a CUDA tensor and never touches the host).  Constants are hparams.py:33-73; they are
 baked into the kernel, there is no `hparams` object to mutate.
 
-The rest of audio.py (load_wav resampling, save_wav, the inverse transforms) is outside the hot
-path and not provided.  As in the reference (wav2lip_train.py:139-141 runs it inside DataLoader
+`load_wav` / `save_wav` (audio.py:9-15) are host-side file helpers, provided so that the reference's scripts
+run unchanged with this module shadowing theirs (inference.py:224 calls `audio.load_wav(path, 16000)`); the
+inverse transforms of audio.py are outside the hot path and not provided.  As in the reference (wav2lip_train.py:139-141 runs it inside DataLoader
 workers), note that a CUDA-backed function must not be called from forked worker processes.
 """
 import ctypes as C
@@ -35,6 +36,44 @@ def _context(device: int):
     if device not in _ctx:
         _ctx[device] = L.Context(device)
     return _ctx[device]
+
+
+def load_wav(path, sr):
+    """audio.py:9-10 `librosa.core.load(path, sr=sr)[0]`: mono float32 in [-1, 1) at `sr` Hz.
+    Uses librosa when it is importable (identical to the reference, resampy kaiser_best included).  Otherwise a
+    scipy.io.wavfile reader with librosa's conventions — integer PCM scaled by 2^-(bits-1), channels averaged — and,
+    only if the file's rate differs from `sr`, scipy.signal.resample_poly (a polyphase Kaiser FIR: NOT bit-identical to
+    resampy's kaiser_best; inference.py:219-221 already makes ffmpeg write 16 kHz files, the common case, where no
+    resampling happens and the samples are exact)."""
+    try:
+        import librosa  # noqa: WPS433
+        return librosa.core.load(path, sr=sr)[0]
+    except ImportError:
+        pass
+    from math import gcd
+
+    from scipy.io import wavfile
+    rate, data = wavfile.read(path)
+    if data.dtype.kind == "i":
+        x = data.astype(np.float32) / np.float32(2 ** (8 * data.dtype.itemsize - 1))
+    elif data.dtype.kind == "u":  # 8-bit PCM is unsigned, offset 128
+        x = (data.astype(np.float32) - 128.0) / 128.0
+    else:
+        x = data.astype(np.float32)
+    if x.ndim > 1:
+        x = x.mean(axis=1, dtype=np.float32)
+    if sr is not None and int(rate) != int(sr):
+        from scipy import signal
+        g = gcd(int(rate), int(sr))
+        x = signal.resample_poly(x.astype(np.float64), int(sr) // g, int(rate) // g).astype(np.float32)
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+def save_wav(wav, path, sr):
+    """audio.py:12-15, verbatim semantics (scales `wav` IN PLACE to int16 full scale, as the reference does)."""
+    from scipy.io import wavfile
+    wav *= 32767 / max(0.01, np.max(np.abs(wav)))
+    wavfile.write(path, sr, wav.astype(np.int16))
 
 
 def num_frames(n_samples: int) -> int:

@@ -225,6 +225,11 @@ struct ConvCfg {
     static_assert(kStages >= 2, "need a pipeline");
 };
 
+// Sticky range flag of the fp16 modes: set by any epilogue that rounds a value beyond the fp16 range (|v| > 65504 ->
+// inf, or a NaN) when it stores an activation.  One instance per device (module-scope __device__ variable); read and
+// cleared through w2l_f16_overflow().  bf16 has fp32's exponent range and never sets it.
+__device__ int g_f16_overflow = 0;
+
 template <bool kBF16>
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     if constexpr (kBF16) {
@@ -232,7 +237,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
         return *reinterpret_cast<uint32_t*>(&h);
     } else {
         __half2 h = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&h);
+        const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
+        // exponent field all ones (inf / NaN) in either half: adding 0x0400 to the magnitude bits carries into bit 15
+        if (((u & 0x7FFF7FFFu) + 0x04000400u) & 0x80008000u) g_f16_overflow = 1;
+        return u;
     }
 }
 template <bool kBF16>

@@ -130,8 +130,8 @@ __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p
             for (int e = 0; e < 2; ++e) {
                 const int n = 2 * i + e;
                 long long j = t * MEL_HOP + n - MEL_NFFT / 2;
-                if (j < 0) j = -j;
-                if (j >= p.L) j = 2 * (p.L - 1) - j;
+                // np.pad(mode="reflect") index folding; clips shorter than n_fft/2 reflect more than once
+                while (j < 0 || j >= p.L) j = j < 0 ? -j : 2 * (p.L - 1) - j;
                 const double x0 = (double)__ldg(p.wav + j);
                 const double y = (j > 0) ? x0 + (-0.97) * (double)__ldg(p.wav + j - 1) : x0;
                 const double w = 0.5 - 0.5 * tw[n <= 400 ? n : MEL_NFFT - n].x;  // periodic Hann: 0.5 - 0.5 cos(2 pi n / 800)

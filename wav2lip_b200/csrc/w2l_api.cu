@@ -94,9 +94,9 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_done[i], cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ctx->ev_out[i], cudaEventDisableTiming);
     }
-    if (e != cudaSuccess) { delete ctx; return fail(W2L_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    if (e != cudaSuccess) { w2l_destroy(ctx); return fail(W2L_ECUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     int r = init_mel_tables(ctx);
-    if (r != W2L_OK) { delete ctx; return r; }
+    if (r != W2L_OK) { const std::string msg = g_err; w2l_destroy(ctx); g_err = msg; return r; }
     {
         // A/B switches, read once per context: W2L_DISABLE_<NAME>=1 turns one specialised path off (tests/test_gpu_variants.py)
         auto enabled = [](const char* name) { const char* v = getenv(name); return !(v && v[0] == '1'); };
@@ -479,7 +479,7 @@ int64_t w2l_mel_num_frames(int64_t n_samples) { return n_samples < 0 ? 0 : 1 + n
 
 int w2l_melspectrogram(w2l_ctx* ctx, const float* wav, int64_t n_samples, float* mel, void* stream) {
     if (!ctx || !wav || !mel) return fail(W2L_EINVAL, "null argument");
-    if (n_samples <= MEL_NFFT / 2) return fail(W2L_EINVAL, "need more than %d samples for reflect padding (got %lld)", MEL_NFFT / 2, (long long)n_samples);
+    if (n_samples < 2) return fail(W2L_EINVAL, "need at least 2 samples (got %lld)", (long long)n_samples);
     DeviceGuard g(ctx->device);
     MelParams p;
     p.wav = wav; p.L = n_samples; p.mel = mel; p.F = w2l_mel_num_frames(n_samples);
@@ -493,8 +493,9 @@ int w2l_melspectrogram(w2l_ctx* ctx, const float* wav, int64_t n_samples, float*
 
 int w2l_melspectrogram_host(w2l_ctx* ctx, const float* wav_h, int64_t n_samples, float* mel_h) {
     if (!ctx || !wav_h || !mel_h) return fail(W2L_EINVAL, "null argument");
-    if (n_samples <= MEL_NFFT / 2) return fail(W2L_EINVAL, "need more than %d samples for reflect padding (got %lld)", MEL_NFFT / 2, (long long)n_samples);
+    if (n_samples < 2) return fail(W2L_EINVAL, "need at least 2 samples (got %lld)", (long long)n_samples);
     DeviceGuard g(ctx->device);
+    CKR(host_drain(ctx, 0));  // the staging buffers below are slot 0 of the asynchronous host pipeline
     const int64_t F = w2l_mel_num_frames(n_samples);
     CKR(ensure_stage(ctx, 0, (size_t)n_samples * 4));
     CKR(ensure_stage(ctx, 4, (size_t)F * MEL_BANDS * 4));
@@ -523,6 +524,19 @@ int w2l_mel_chunks(w2l_ctx* ctx, const float* mel, int64_t n_frames, double fps,
     mel_chunk_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(mel, n_frames, 80.0 / fps, (int)n_chunks, chunks);
     ctx->launches++;
     CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int w2l_f16_overflow(w2l_ctx* ctx, int clear, int* flag, void* stream) {
+    if (!ctx || !flag) return fail(W2L_EINVAL, "null argument");
+    DeviceGuard g(ctx->device);
+    CK(cudaStreamSynchronize((cudaStream_t)stream));
+    CK(cudaStreamSynchronize(ctx->s_side));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int v = 0;
+    CK(cudaMemcpyFromSymbol(&v, g_f16_overflow, sizeof(int)));
+    *flag = v;
+    if (clear && v) { const int z = 0; CK(cudaMemcpyToSymbol(g_f16_overflow, &z, sizeof(int))); }
     return W2L_OK;
 }
 

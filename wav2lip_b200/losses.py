@@ -13,10 +13,14 @@ import torch
 from . import _lib
 
 
-def _ctx(t: torch.Tensor) -> "_lib.Context":
+def _ctx(t: torch.Tensor, *others) -> "_lib.Context":
+    """Context of t's device; every other tensor whose pointer crosses the C-ABI must live on that same device."""
     if not t.is_cuda:
         raise _lib.W2LError("wav2lip_b200 has no CPU path: tensors must be on a CUDA device")
     dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    for o in others:
+        if o is not None and (not o.is_cuda or (o.device.index if o.device.index is not None else torch.cuda.current_device()) != dev):
+            raise _lib.W2LError(f"expected every tensor on cuda:{dev}, got one on {o.device}")
     c = _CTX.get(dev)
     if c is None:
         c = _CTX[dev] = _lib.Context(dev)
@@ -42,7 +46,7 @@ def cosine_loss(a, v, y=None):
     out = torch.empty((), device=a.device, dtype=torch.float32)
     if B == 0:
         return out.fill_(float("nan"))   # nn.BCELoss over an empty batch: mean of nothing
-    ctx = _ctx(a)
+    ctx = _ctx(a, v, y)
     stream = torch.cuda.current_stream(a.device).cuda_stream
     _lib.check(ctx.lib.w2l_cosine_bce_loss(ctx.h, C.c_void_p(a.data_ptr()), C.c_void_p(v.data_ptr()),
                                            C.c_void_p(y.data_ptr()) if y is not None else None, B, D,
@@ -57,17 +61,26 @@ def recon_loss(g, gt):
     out = torch.empty((), device=g.device, dtype=torch.float32)
     if g.numel() == 0:
         return out.fill_(float("nan"))
-    ctx = _ctx(g)
+    ctx = _ctx(g, gt)
     stream = torch.cuda.current_stream(g.device).cuda_stream
     _lib.check(ctx.lib.w2l_l1_loss(ctx.h, C.c_void_p(g.data_ptr()), C.c_void_p(gt.data_ptr()), g.numel(),
                                    C.c_void_p(out.data_ptr()), C.c_void_p(stream)))
     return out
 
 
-def get_sync_loss(syncnet, mel, g):
+def get_sync_loss(syncnet, mel, g, expert_training: bool = False):
     """syncnet: a wav2lip_b200.models.SyncNet_color in eval mode; mel (B,1,80,16); g (B,3,5,96,96).
-    Note: the reference scripts never call .eval() on their expert (wav2lip_train.py:187-189), so there its BatchNorm
-    uses batch statistics; here the expert runs on its running statistics (eval mode) — batch-statistics BatchNorm is
-    part of the training row that is not built."""
+
+    DIVERGENCE from the reference, made explicit in the signature: the reference scripts never call .eval() on their
+    expert (wav2lip_train.py:187-189), so THEIR get_sync_loss runs the expert's BatchNorm on batch statistics (and moves
+    its running averages).  This forward-value function runs the expert on its running statistics (`expert_training=
+    False`), so the number it returns is NOT the one the reference logs as `sync_loss`.  The reference's behaviour
+    (batch statistics, differentiable w.r.t. g) is what wav2lip_b200.training.TrainStep computes inside the training
+    step; asking for it here raises."""
+    if expert_training:
+        raise NotImplementedError(
+            "get_sync_loss(expert_training=True) — the reference's batch-statistics expert — is computed inside "
+            "wav2lip_b200.training.TrainStep (which also back-propagates it); this evaluation helper runs the expert "
+            "in eval mode only")
     a, v = syncnet.forward_frames(mel, g)
     return cosine_loss(a, v, None)

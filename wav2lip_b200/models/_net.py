@@ -1,6 +1,7 @@
 """Shared machinery of the three network mirrors: module tree from the C-side table, weight
 hand-off to the context, and the no-fallback guards."""
 import ctypes as C
+import os
 
 import torch
 from torch import nn
@@ -71,10 +72,15 @@ class NativeNet(nn.Module):
         return tuple(t._version for t in ts)
 
     def _ensure(self, ref: torch.Tensor):
+        if self.training and torch.is_grad_enabled() and self._wants_grad():
+            raise NotImplementedError(
+                f"{type(self).__name__}: a differentiable training-mode forward goes through wav2lip_b200.training "
+                "(TrainStep / the autograd bridge), not through the inference plan: call .eval() and torch.no_grad() "
+                "here. (A detached result would silently drop this term's gradient.)")
         if self.training and self.NET != _lib.NET_DISC:
             raise NotImplementedError(
-                "training-mode forward (BatchNorm batch statistics + autograd) is the next row of the scope "
-                "table and is not built yet: call .eval() and torch.no_grad()")
+                "the inference plan runs BatchNorm on its running statistics (eval mode); batch-statistics forward "
+                "+ backward live in wav2lip_b200.training: call .eval() for this entry point")
         dev = self._device_index(ref)
         if self._w2l_ctx is None or self._w2l_ctx.device != dev:
             self._w2l_ctx = _lib.Context(dev, self.precision)
@@ -93,7 +99,39 @@ class NativeNet(nn.Module):
             stream = torch.cuda.current_stream(ref.device).cuda_stream
             self._w2l_ctx.load_weights(self.NET, tensors, stream)
             self._w2l_key = key
+            self._w2l_range_checked = False
         return self._w2l_ctx
+
+    def _wants_grad(self) -> bool:
+        return any(p.requires_grad for p in self.parameters())
+
+    def _same_device(self, ctx, *tensors):
+        """Every tensor whose data_ptr() crosses the C-ABI must live on the context's device: a CPU tensor or a tensor
+        of another GPU would be dereferenced as a foreign pointer (illegal address -> sticky CUDA error).  The reference
+        raises a device-mismatch RuntimeError in the same situation; so do we, before anything is launched."""
+        for t in tensors:
+            if t is None:
+                continue
+            idx = t.device.index if t.device.index is not None else (torch.cuda.current_device() if t.is_cuda else -1)
+            if not t.is_cuda or idx != ctx.device:
+                raise _lib.W2LError(
+                    f"{type(self).__name__}: expected every input on cuda:{ctx.device}, got a tensor on {t.device} "
+                    "(wav2lip_b200 has no CPU path and does not copy between devices)")
+
+    def _range_guard(self, ctx, stream):
+        """fp16 range guard (include/w2l.h: w2l_f16_overflow): checked once after the first forward that follows a
+        weight (re)load — or after every forward with W2L_CHECK_RANGE=always — so a checkpoint whose activations leave
+        the fp16 range raises instead of returning inf/NaN-poisoned results.  Costs one stream sync when it runs."""
+        if self.precision == _lib.PREC_BF16:
+            return
+        if getattr(self, "_w2l_range_checked", False) and os.environ.get("W2L_CHECK_RANGE", "") != "always":
+            return
+        self._w2l_range_checked = True
+        if ctx.f16_overflow(clear=True, stream=stream):
+            raise _lib.W2LError(
+                f"{type(self).__name__}: an activation left the fp16 range (|v| > 65504) with these weights/inputs; "
+                "the result is not trustworthy. Run this checkpoint with bf16 operands: set "
+                f"`{type(self).__name__}.precision = wav2lip_b200._lib.PREC_BF16` before the first forward.")
 
     @staticmethod
     def _in(t: torch.Tensor) -> torch.Tensor:

@@ -18,6 +18,7 @@ class SyncNet_color(NativeNet):
 
     def forward(self, audio_sequences, face_sequences):
         ctx = self._ensure(face_sequences)
+        self._same_device(ctx, audio_sequences, face_sequences)
         mel, face = self._in(audio_sequences), self._in(face_sequences)
         B = face.shape[0]
         if tuple(mel.shape) != (B, 1, 80, 16) or tuple(face.shape[1:]) != (15, 48, 96):
@@ -28,6 +29,7 @@ class SyncNet_color(NativeNet):
             return a, v
         stream = torch.cuda.current_stream(face.device).cuda_stream
         _lib.check(ctx.lib.w2l_syncnet_forward(ctx.h, self._p(mel), self._p(face), self._p(a), self._p(v), B, C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
         return a, v
 
     def forward_frames(self, audio_sequences, frames):
@@ -35,6 +37,7 @@ class SyncNet_color(NativeNet):
         frames (B,3,T=5,96,96) -> lower half, T frames stacked on channels -> (audio_embedding, face_embedding).
         Same result as forward(mel, cat([frames[:, :, i, 48:] for i in range(5)], 1)) without materialising the stack."""
         ctx = self._ensure(frames)
+        self._same_device(ctx, audio_sequences, frames)
         mel, fr = self._in(audio_sequences), self._in(frames)
         B = fr.shape[0]
         if fr.dim() != 5 or tuple(fr.shape[1:]) != (3, 5, 96, 96) or tuple(mel.shape) != (B, 1, 80, 16):
@@ -45,4 +48,5 @@ class SyncNet_color(NativeNet):
             return a, v
         stream = torch.cuda.current_stream(fr.device).cuda_stream
         _lib.check(ctx.lib.w2l_syncnet_forward_frames(ctx.h, self._p(mel), self._p(fr), self._p(a), self._p(v), B, 5, C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
         return a, v

@@ -26,6 +26,7 @@ class Wav2Lip(NativeNet):
 
     def forward(self, audio_sequences, face_sequences):
         ctx = self._ensure(face_sequences)
+        self._same_device(ctx, audio_sequences, face_sequences)
         mel, face = self._in(audio_sequences), self._in(face_sequences)
         if face.dim() > 4:  # wav2lip.py:91-94
             B, _, T, H, W = face.shape
@@ -41,6 +42,7 @@ class Wav2Lip(NativeNet):
             return out
         stream = torch.cuda.current_stream(face.device).cuda_stream
         _lib.check(ctx.lib.w2l_generator_forward(ctx.h, self._p(mel), self._p(face), self._p(out), B, T, C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
         return out
 
 
@@ -53,6 +55,7 @@ class Wav2Lip(NativeNet):
         if face_crops_u8.dtype != torch.uint8 or face_crops_u8.dim() != 4 or tuple(face_crops_u8.shape[1:]) != (96, 96, 3):
             raise ValueError(f"expected uint8 (N,96,96,3) crops, got {face_crops_u8.dtype} {tuple(face_crops_u8.shape)}")
         N = face_crops_u8.shape[0]
+        self._same_device(ctx, mel_batch, face_crops_u8)
         mel = self._in(mel_batch)
         if tuple(mel.shape) != (N, 1, 80, 16):
             raise ValueError(f"expected mel (N,1,80,16), got {tuple(mel.shape)}")
@@ -62,6 +65,7 @@ class Wav2Lip(NativeNet):
             return out
         stream = torch.cuda.current_stream(faces.device).cuda_stream
         _lib.check(ctx.lib.w2l_generator_forward_u8(ctx.h, self._p(mel), self._p(faces), self._p(out), N, C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
         return out
 
 
@@ -138,6 +142,7 @@ class Wav2Lip_disc_qual(NativeNet):
 
     def forward(self, face_sequences):
         ctx = self._ensure(face_sequences)
+        self._same_device(ctx, face_sequences)
         x = self._in(face_sequences)
         if x.dim() != 5 or x.shape[1] != 3 or tuple(x.shape[3:]) != (96, 96):
             raise ValueError(f"expected (B,3,T,96,96), got {tuple(x.shape)}")
@@ -147,6 +152,7 @@ class Wav2Lip_disc_qual(NativeNet):
             return out
         stream = torch.cuda.current_stream(x.device).cuda_stream
         _lib.check(ctx.lib.w2l_disc_forward(ctx.h, self._p(x), self._p(out), B, T, C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
         return out
 
     def perceptual_forward(self, false_face_sequences):
