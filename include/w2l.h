@@ -188,6 +188,73 @@ int w2l_set_debug(w2l_ctx* ctx, int keep_all_layer_outputs);
 /* the kernel's own (80 x 401) Slaney mel filterbank, dense fp32, written to HOST memory */
 int w2l_mel_basis_host(float* out_host);
 
+/* ---- training step (scope row f1): wav2lip_train.py:210-231, color_syncnet_train.py:146-163, hq_wav2lip_train.py:213-255 ----
+ * Train-mode forward (BatchNorm on batch statistics over the T*B flatten, conv.py:8-11 / wav2lip.py:93-94; running
+ * averages updated with momentum 0.1) and backward through every block, as kernels: conv / dgrad on the tcgen05 conv
+ * kernels, wgrad on a tcgen05 kernel whose K dimension is the pixel index, BatchNorm / ReLU / residual passes,
+ * loss gradients, multi-tensor Adam, bucketed NCCL all-reduce of the gradients.  bf16 operands, fp32 accumulation,
+ * fp32 master parameters and gradients (the context must be created with W2L_PREC_BF16).
+ *
+ * w2l_train_bind replaces `optimizer = optim.Adam([p for p in model.parameters() ...])` + the module's own tensors
+ * (wav2lip_train.py:356-360): it hands the context, by reference state_dict name, the caller's fp32 device tensors —
+ * parameters (value + gradient pointer; NULL gradient = frozen, wav2lip_train.py:188-189) and BatchNorm buffers
+ * (running_mean / running_var, gradient NULL).  The pointers must stay valid; values are re-read (and the 16-bit weight
+ * slabs re-packed) at every training forward, gradients are written by the backward, running averages are updated in
+ * place.  Gradients laid out contiguously (one arena in state_dict order) are all-reduced as three large buckets. */
+#define W2L_TRAIN_WGRAD           1   /* compute parameter gradients into the bound gradient tensors */
+#define W2L_TRAIN_ACCUMULATE      2   /* add to the bound gradient tensors instead of overwriting (two backward() calls, hq_wav2lip_train.py:248-253) */
+#define W2L_TRAIN_INPUT_GRAD      4   /* the plan also produces dL/d(input frames) (expert / discriminator inside a generator step) */
+#define W2L_TRAIN_NO_STAT_UPDATE  8   /* leave running_mean / running_var untouched */
+int w2l_train_bind(w2l_ctx* ctx, int net, int n_tensors, const char* const* names, void* const* value_ptrs,
+                   void* const* grad_ptrs, const int64_t* numels);
+
+/* Train-mode forward; keeps the tape (block inputs, pre-BatchNorm outputs, outputs) for w2l_train_backward.
+ *   W2L_NET_GENERATOR: in0 = mel, in1 = face (4-D with T == 0 or 5-D with T > 0, as w2l_generator_forward), out0 = g.
+ *                      out0 must stay valid until the backward (the head's backward re-reads it).
+ *   W2L_NET_SYNCNET  : in0 = mel (B,1,80,16); in1 = face (B,15,48,96) [T == 0] or frames (B,3,5,96,96) [T == 5];
+ *                      out0 = audio_embedding, out1 = face_embedding (B,512), L2-normalised.
+ *   W2L_NET_DISC     : in0 = frames (B,3,T,96,96), out0 = prob (B*T,1) t-major. */
+int w2l_train_forward(w2l_ctx* ctx, int net, const float* in0_dev, const float* in1_dev, float* out0_dev, float* out1_dev,
+                      int B, int T, int flags, void* stream);
+
+/* Backward of the last w2l_train_forward of `net`.  d0 (/ d1) = dL/d out0 (/ out1) fp32, same shapes; with
+ * W2L_TRAIN_WGRAD the bound gradient tensors receive dL/dparameter (`loss.backward()`, wav2lip_train.py:230);
+ * dinput (needs W2L_TRAIN_INPUT_GRAD at the forward) receives dL/d in1 (SyncNet: frames (B,3,5,96,96) — zero in the
+ * upper half — or face (B,15,48,96)) or dL/d in0 (disc frames), fp32. */
+int w2l_train_backward(w2l_ctx* ctx, int net, const float* d0_dev, const float* d1_dev, float* dinput_dev, int flags,
+                       void* stream);
+
+/* Replaces `optimizer.step()` (torch.optim.Adam, no weight decay / amsgrad; wav2lip_train.py:231, :357-360) on every
+ * bound tensor of `net` that has a gradient: one multi-tensor kernel; moments live in the context. */
+int w2l_adam_step(w2l_ctx* ctx, int net, float lr, float beta1, float beta2, float eps, void* stream);
+
+/* One whole iteration of wav2lip_train.py:210-231 on the bound generator and (frozen, train-mode as in the scripts,
+ * :187-189) expert: g = model(indiv_mels, x); sync_loss = get_sync_loss(mel, g) if syncnet_wt > 0; l1 = L1(g, gt);
+ * loss = syncnet_wt*sync + (1-syncnet_wt)*l1; backward; [gradient all-reduce, overlapped]; Adam(lr, (0.9,0.999), 1e-8).
+ *   indiv_mels (B,T,1,80,16), x (B,6,T,96,96), mel (B,1,80,16), gt (B,3,T,96,96); losses_dev: 4 floats on the device
+ *   [sync_loss, l1, 0, loss] or NULL. */
+int w2l_wav2lip_train_step(w2l_ctx* ctx, const float* indiv_mels_dev, const float* x_dev, const float* mel_dev,
+                           const float* gt_dev, int B, int T, float syncnet_wt, float lr, float* losses_dev, void* stream);
+/* copies the generator output g (B,3,T,96,96) of the last fused step into out_dev (n floats) */
+int w2l_train_last_output(w2l_ctx* ctx, float* out_dev, int64_t n, void* stream);
+/* algorithmic forward FLOPs of the last training plan of `net` (2 x true MACs of its convs) */
+double w2l_train_flops(w2l_ctx* ctx, int net);
+
+/* Data-parallel training: the gradient all-reduce is the one collective of the system.  NCCL is
+ * resolved at run time from the process (torch loads libnccl.so.2); rank 0 creates the 128-byte unique id, the host
+ * side broadcasts it (torch.distributed), every rank calls w2l_comm_init.  w2l_wav2lip_train_step then averages the
+ * gradients over the ranks (ncclAvg) in three buckets launched on a side stream as the backward completes them. */
+int w2l_comm_unique_id(w2l_ctx* ctx, char* id128);
+int w2l_comm_init(w2l_ctx* ctx, const char* id128, int rank, int world);
+
+/* One conv.py block in train mode, forward + backward (operator-level entry of the per-geometry gradient tests):
+ *   x (N,cin,H,W), dy (N,cout,Ho,Wo) fp32 -> y, dx (same layouts; dy/dx/dw may be NULL), dw in the parameter's own
+ *   layout, db, dgamma, dbeta; bn_mean / bn_var (running averages) are updated in place when given. */
+int w2l_conv_block_train(w2l_ctx* ctx, const w2l_layer_info* spec, const float* x_dev, int N, int H, int W,
+                         float* weight_dev, float* bias_dev, float* bn_weight_dev, float* bn_bias_dev, float* bn_mean_dev,
+                         float* bn_var_dev, const float* dy_dev, float* y_dev, float* dx_dev, float* dw_dev, float* db_dev,
+                         float* dgamma_dev, float* dbeta_dev, void* stream);
+
 /* Range guard of the fp16 modes (W2L_PREC_F16 / _F32X): every epilogue that stores an activation sets a sticky
  * per-device flag when the rounded value leaves the fp16 range (|v| > 65504 -> inf, or NaN).  Synchronises `stream`,
  * writes the flag to *flag (0 = every activation stored so far was finite) and, if `clear`, resets it.  A checkpoint

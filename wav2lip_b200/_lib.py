@@ -16,6 +16,7 @@ W2L_OK, W2L_EINVAL, W2L_ENODEV, W2L_ECUDA, W2L_ENOMEM, W2L_ESTATE = 0, -1, -2, -
 NET_GENERATOR, NET_SYNCNET, NET_DISC = 0, 1, 2
 BLOCK_CONV_BN_RELU, BLOCK_CONVT_BN_RELU, BLOCK_CONV_LRELU, BLOCK_CONV_PLAIN = 0, 1, 2, 3
 PREC_F16, PREC_BF16, PREC_F32X = 0, 1, 2
+TRAIN_WGRAD, TRAIN_ACCUMULATE, TRAIN_INPUT_GRAD, TRAIN_NO_STAT_UPDATE = 1, 2, 4, 8
 
 # every symbol include/w2l.h declares (tests/test_abi.py checks the header against this list)
 EXPORTS = [
@@ -28,6 +29,8 @@ EXPORTS = [
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
     "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
     "w2l_f16_overflow",
+    "w2l_train_bind", "w2l_train_forward", "w2l_train_backward", "w2l_adam_step", "w2l_wav2lip_train_step",
+    "w2l_train_last_output", "w2l_train_flops", "w2l_comm_unique_id", "w2l_comm_init", "w2l_conv_block_train",
 ]
 
 
@@ -95,6 +98,18 @@ def get_lib() -> C.CDLL:
     lib.w2l_device_bytes.restype = i64
     lib.w2l_profile_plan.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.w2l_f16_overflow.argtypes = [vp, i32, C.POINTER(i32), vp]
+    f32 = C.c_float
+    lib.w2l_train_bind.argtypes = [vp, i32, i32, C.POINTER(cp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
+    lib.w2l_train_forward.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]
+    lib.w2l_train_backward.argtypes = [vp, i32, vp, vp, vp, i32, vp]
+    lib.w2l_adam_step.argtypes = [vp, i32, f32, f32, f32, f32, vp]
+    lib.w2l_wav2lip_train_step.argtypes = [vp, vp, vp, vp, vp, i32, i32, f32, f32, vp, vp]
+    lib.w2l_train_last_output.argtypes = [vp, vp, i64, vp]
+    lib.w2l_train_flops.argtypes = [vp, i32]
+    lib.w2l_train_flops.restype = C.c_double
+    lib.w2l_comm_unique_id.argtypes = [vp, C.c_char_p]
+    lib.w2l_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
+    lib.w2l_conv_block_train.argtypes = [vp, C.POINTER(LayerInfo), vp, i32, i32, i32] + [vp] * 14
     for name in EXPORTS:
         getattr(lib, name)  # AttributeError here == header / library mismatch
     if lib.w2l_abi_version() != 1:

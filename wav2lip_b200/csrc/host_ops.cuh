@@ -66,10 +66,13 @@ static void fill_epi(EpiParams* e, const ConvArgs& a) {
         e->out_sx = (long long)a.osx * oCs;
     }
     if (a.res) {
-        e->res = a.res->ptr();
-        e->res_sn = (long long)a.res->H * a.res->W * a.res->Cs;
-        e->res_sy = (long long)a.res->W * a.res->Cs;
-        e->res_sx = a.res->Cs;
+        // same pixel mapping as the output: logical pixel (y, x) of a phase launch is pixel (y*osy + phy, x*osx + phx)
+        // (the forward never adds a residual to a transposed conv; the dgrad of a strided conv does: the skip gradient)
+        const long long rCs = a.res->Cs, rW = a.res->W;
+        e->res = a.res->ptr() + ((long long)a.phy * rW + a.phx) * rCs;
+        e->res_sn = (long long)a.res->H * rW * rCs;
+        e->res_sy = (long long)a.osy * rW * rCs;
+        e->res_sx = (long long)a.osx * rCs;
     }
     e->scale = a.scale + a.ch_off;
     e->shift = a.shift + a.ch_off;
@@ -390,7 +393,7 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
 }
 
 // Conv2dTranspose k3 s2 p1 op1 with 64 output channels: all four phases in one launch (convt_fused.cuh)
-static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const LayerW& lw, const Act& in, const Act& out) {
+static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const LayerW& lw, const Act& in, const Act& out, int act = ACT_RELU) {
     EncodeTiledFn enc = get_encode_fn();
     if (!enc) return fail(W2L_ENODEV, "cuTensorMapEncodeTiled is not available");
     const PackedW& w = lw.ph.back();  // all 9 taps, grouped by input shift (load_layer)
@@ -434,7 +437,7 @@ static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const Lay
     t.stages = std::min(kCtMaxStages, (kCtSmemMax - fixed) / stage_bytes);
     if (t.stages < 2) return fail(W2L_EINVAL, "%s: fused convT does not fit shared memory", L.name.c_str());
     op.dyn_smem = t.stages * stage_bytes + fixed;
-    t.act = ACT_RELU;
+    t.act = act;
     CK(cudaDeviceSynchronize());
     CK(cudaMemcpy(t.cscale, lw.scale, kCtBN * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(t.cshift, lw.shift, kCtBN * 4, cudaMemcpyDeviceToHost));
@@ -446,13 +449,15 @@ static int make_convt_fused_op(w2l_ctx* ctx, Plan* pl, const Layer& L, const Lay
 }
 
 // Emit the launches of one block (conv / convT) of a spec table.
+// act_override >= 0 replaces the block kind's activation (training: the conv stores the pre-BatchNorm output; dgrad: none).
 static int emit_block(w2l_ctx* ctx, Plan* pl, const NetW& nw, int li, const Layer& L, const Act& in, const Act& out,
-                      const Act* res, bool head = false, int head_B = 1, int head_T = 1) {
+                      const Act* res, bool head = false, int head_B = 1, int head_T = 1, int act_override = -1) {
     const LayerW& lw = nw.layers[li];
     ConvArgs a;
     a.in = in; a.out = out; a.res = res;
     a.scale = lw.scale; a.shift = lw.shift;
     a.act = (L.kind == W2L_BLOCK_CONV_LRELU) ? ACT_LRELU : (L.kind == W2L_BLOCK_CONV_PLAIN ? ACT_NONE : ACT_RELU);
+    if (act_override >= 0) a.act = act_override;
     a.cout = L.cout;
     a.head = head; a.head_w = nw.head_w; a.head_b = nw.head_b; a.head_B = head_B; a.head_T = head_T;
     if (L.kind != W2L_BLOCK_CONVT_BN_RELU) {
@@ -476,9 +481,9 @@ static int emit_block(w2l_ctx* ctx, Plan* pl, const NetW& nw, int li, const Laye
         a.macs_per_pixel = (double)L.cin * L.cout * L.kh * L.kw;
         return make_conv_op(ctx, pl, a);
     }
-    if (lw.has_all_taps && ctx->use_ctfused && in.W >= 8 && in.H >= 8 &&
+    if (lw.has_all_taps && ctx->use_ctfused && in.W >= 8 && in.H >= 8 && !res && out.H == 2 * in.H && out.W == 2 * in.W &&
         (double)in.W * in.H / ((double)((in.W + 7) / 8) * ((in.H + 15) / 16) * kTileM) >= 0.6 && !out.f32)
-        return make_convt_fused_op(ctx, pl, L, lw, in, out);
+        return make_convt_fused_op(ctx, pl, L, lw, in, out, a.act);
     const size_t nph = lw.ph.size() - (lw.has_all_taps ? 1 : 0);
     for (size_t i = 0; i < nph; ++i) {
         const PackedW& w = lw.ph[i];

@@ -155,7 +155,13 @@ struct Plan {
     bool has_side = false;         // some ops run on the side stream
 };
 
+struct FoldJob { const float* bias; int cout, reps, n_pad; float* scale; float* shift; };  // nonorm blocks: shift = conv bias
+struct TrainState;  // host_train.cuh
+
 struct w2l_ctx {
+    std::vector<PackParams>* pack_rec = nullptr;  // when set, pack_taps records its jobs (training re-packs every step)
+    std::vector<FoldJob>* fold_rec = nullptr;
+    TrainState* train = nullptr;
     int device = 0;
     bool bf16 = false;
     bool x2 = false;        // W2L_PREC_F32X: split fp16 operands (hi + lo), generic kernel only

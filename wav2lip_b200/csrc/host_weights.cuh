@@ -43,6 +43,7 @@ static int pack_taps(w2l_ctx* ctx, PackedW* pw, const float* src, int cout, int 
         pw->nslabs = pp.ntaps * planes;
     }
     const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+    if (ctx->pack_rec) ctx->pack_rec->push_back(pp);  // training: the same job is replayed after every optimizer step
     for (int pl_ = 0; pl_ < planes; ++pl_) {  // hi slabs, then (split-operand mode) the lo slabs w - fp16(w)
         pp.lo = pl_;
         if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
@@ -163,6 +164,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
     CKR(dev_alloc(&sh, (size_t)n_pad * 4));
     lw->scale = (float*)sc; lw->shift = (float*)sh; lw->n_scale = n_pad;
     fold_bn_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, 1e-5f, L.cout, reps, n_pad, lw->scale, lw->shift);
+    if (ctx->fold_rec && bias) ctx->fold_rec->push_back(FoldJob{bias, L.cout, reps, n_pad, lw->scale, lw->shift});
     ctx->launches++;
     CK(cudaGetLastError());
     lw->loaded = true;

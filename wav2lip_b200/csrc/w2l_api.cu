@@ -10,6 +10,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <functional>
 #include <map>
 #include <memory>
 #include <string>
@@ -23,6 +25,8 @@
 #include "convt_fused.cuh"
 #include "mel.cuh"
 #include "netspec.h"
+#include "train_kernels.cuh"
+#include "wgrad_tcgen05.cuh"
 
 using namespace w2l;
 
@@ -32,6 +36,7 @@ using namespace w2l;
 #include "host_weights.cuh"
 #include "host_plans.cuh"
 #include "host_mel_tables.h"
+#include "host_train.cuh"
 
 // ------------------------------------------------------------------------------------------------
 // C-ABI
@@ -130,6 +135,7 @@ int w2l_destroy(w2l_ctx* ctx) {
     if (!ctx) return W2L_OK;
     DeviceGuard g(ctx->device);
     cudaDeviceSynchronize();
+    free_train_state(ctx);
     for (auto& kv : ctx->plans) free_plan(kv.second.get());
     for (int n = 0; n < 3; ++n) {
         for (auto& lw : ctx->nets[n].layers) free_layer(lw);
@@ -538,6 +544,269 @@ int w2l_f16_overflow(w2l_ctx* ctx, int clear, int* flag, void* stream) {
     *flag = v;
     if (clear && v) { const int z = 0; CK(cudaMemcpyToSymbol(g_f16_overflow, &z, sizeof(int))); }
     return W2L_OK;
+}
+
+
+// ================================================================================================
+// training
+// ================================================================================================
+int w2l_train_bind(w2l_ctx* ctx, int net, int n_tensors, const char* const* names, void* const* value_ptrs, void* const* grad_ptrs,
+                   const int64_t* numels) {
+    if (!ctx || !names || !value_ptrs || !numels) return fail(W2L_EINVAL, "null argument");
+    if (net < 0 || net > 2) return fail(W2L_EINVAL, "unknown net %d", net);
+    DeviceGuard g(ctx->device);
+    TrainState* ts = train_state(ctx);
+    CK(cudaDeviceSynchronize());
+    // plans bake the bound pointers: drop the ones of this net
+    for (auto it = ts->plans.begin(); it != ts->plans.end();) {
+        if (it->second->net == net) { free_train_plan(it->second.get()); it = ts->plans.erase(it); }
+        else ++it;
+    }
+    ts->last[net] = nullptr;
+    AdamSlot& a = ts->adam[net];
+    for (float* p : a.m) cudaFree(p);
+    for (float* p : a.v) cudaFree(p);
+    if (a.dev) cudaFree(a.dev);
+    a = AdamSlot();
+    ts->bound[net].clear();
+    for (int i = 0; i < n_tensors; ++i) {
+        std::string nm = names[i];
+        if (nm.rfind("module.", 0) == 0) nm = nm.substr(7);
+        ts->bound[net][nm] = ParamRef{(float*)value_ptrs[i], grad_ptrs ? (float*)grad_ptrs[i] : nullptr, (long long)numels[i]};
+    }
+    ts->is_bound[net] = true;
+    return ensure_train_scratch(ctx, 1, 1);
+}
+
+int w2l_train_forward(w2l_ctx* ctx, int net, const float* in0, const float* in1, float* out0, float* out1, int B, int T, int flags,
+                      void* stream) {
+    if (!ctx || !in0 || !out0) return fail(W2L_EINVAL, "null argument");
+    if (net < 0 || net > 2 || B <= 0 || T < 0) return fail(W2L_EINVAL, "bad argument net=%d B=%d T=%d", net, B, T);
+    if (net != W2L_NET_DISC && !in1) return fail(W2L_EINVAL, "null argument");
+    if (net == W2L_NET_SYNCNET && (!out1 || (T != 0 && T != 5))) return fail(W2L_EINVAL, "SyncNet_color: T must be 0 (stacked faces) or 5 (frames)");
+    if (net == W2L_NET_DISC && T <= 0) return fail(W2L_EINVAL, "Wav2Lip_disc_qual takes (B,3,T,96,96)");
+    DeviceGuard g(ctx->device);
+    TrainPlan* tp;
+    const bool wg = net == W2L_NET_GENERATOR ? true : (flags & TRAIN_WGRAD) != 0;
+    const bool ig = net == W2L_NET_GENERATOR ? false : (flags & TRAIN_INPUT_GRAD) != 0;
+    CKR(get_train_plan(ctx, net, B, T, wg, ig, &tp));
+    return train_forward(ctx, tp, in0, in1, out0, out1, flags, (cudaStream_t)stream);
+}
+
+int w2l_train_backward(w2l_ctx* ctx, int net, const float* d0, const float* d1, float* dinput, int flags, void* stream) {
+    if (!ctx || !d0) return fail(W2L_EINVAL, "null argument");
+    if (net < 0 || net > 2) return fail(W2L_EINVAL, "unknown net %d", net);
+    DeviceGuard g(ctx->device);
+    TrainState* ts = train_state(ctx);
+    TrainPlan* tp = ts->last[net];
+    if (!tp) return fail(W2L_ESTATE, "backward of net %d before a training forward", net);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (net == W2L_NET_SYNCNET && !d1) return fail(W2L_EINVAL, "null argument");
+    if (dinput && !tp->input_grad) return fail(W2L_ESTATE, "the forward was not run with W2L_TRAIN_INPUT_GRAD");
+    if (net == W2L_NET_GENERATOR) flags |= TRAIN_WGRAD;
+    CKR(train_backward(ctx, tp, d0, d1, flags, st));
+    if (dinput) {
+        if (net == W2L_NET_SYNCNET && tp->T == 0) {
+            const long long total = (long long)tp->N * 15 * 48 * 96;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+            if (ctx->bf16) export_grad_kernel<true><<<blocks, 256, 0, st>>>(tp->dface_in.ptr(), tp->dface_in.Cs, dinput, tp->N, 48, 96, 15);
+            else export_grad_kernel<false><<<blocks, 256, 0, st>>>(tp->dface_in.ptr(), tp->dface_in.Cs, dinput, tp->N, 48, 96, 15);
+        } else {
+            GenLossGradParams lp;
+            memset(&lp, 0, sizeof(lp));
+            lp.dg = dinput; lp.B = tp->B; lp.T = tp->T;
+            if (net == W2L_NET_SYNCNET) lp.dsync = tp->dface_in.ptr(); else lp.ddisc = tp->dframes_in.ptr();
+            const long long total = (long long)tp->B * 3 * tp->T * 9216;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+            if (ctx->bf16) gen_loss_grad_kernel<true><<<blocks, 256, 0, st>>>(lp);
+            else gen_loss_grad_kernel<false><<<blocks, 256, 0, st>>>(lp);
+        }
+        ctx->launches++;
+        CK(cudaGetLastError());
+    }
+    return W2L_OK;
+}
+
+int w2l_adam_step(w2l_ctx* ctx, int net, float lr, float beta1, float beta2, float eps, void* stream) {
+    if (!ctx || net < 0 || net > 2) return fail(W2L_EINVAL, "bad argument");
+    DeviceGuard g(ctx->device);
+    TrainState* ts = train_state(ctx);
+    if (!ts->is_bound[net]) return fail(W2L_ESTATE, "adam: net %d is not bound", net);
+    return adam_step(ctx, net, lr, beta1, beta2, eps, 1.0f, (cudaStream_t)stream);
+}
+
+int w2l_comm_unique_id(w2l_ctx* ctx, char* id128) {
+    if (!ctx || !id128) return fail(W2L_EINVAL, "null argument");
+    TrainState* ts = train_state(ctx);
+    NcclGetUniqueIdFn f = (NcclGetUniqueIdFn)nccl_sym(ts, "ncclGetUniqueId");
+    if (!f) return fail(W2L_ENODEV, "NCCL not found in the process (libnccl.so.2)");
+    const int rc = f(id128);
+    if (rc != 0) return fail(W2L_ECUDA, "ncclGetUniqueId failed (%d)", rc);
+    return W2L_OK;
+}
+
+int w2l_comm_init(w2l_ctx* ctx, const char* id128, int rank, int world) {
+    if (!ctx || !id128 || world < 1 || rank < 0 || rank >= world) return fail(W2L_EINVAL, "bad argument");
+    DeviceGuard g(ctx->device);
+    TrainState* ts = train_state(ctx);
+    if (ts->comm) return fail(W2L_ESTATE, "communicator already initialised");
+    ts->rank = rank; ts->world = world;
+    if (world == 1) return W2L_OK;
+    NcclCommInitRankFn init = (NcclCommInitRankFn)nccl_sym(ts, "ncclCommInitRank");
+    ts->all_reduce = (NcclAllReduceFn)nccl_sym(ts, "ncclAllReduce");
+    ts->comm_destroy = (NcclCommDestroyFn)nccl_sym(ts, "ncclCommDestroy");
+    ts->err_string = (NcclGetErrorStringFn)nccl_sym(ts, "ncclGetErrorString");
+    if (!init || !ts->all_reduce) return fail(W2L_ENODEV, "NCCL not found in the process (libnccl.so.2)");
+    NcclId id;
+    memcpy(id.bytes, id128, 128);
+    const int rc = init(&ts->comm, world, id, rank);
+    if (rc != 0) { ts->comm = nullptr; return fail(W2L_ECUDA, "ncclCommInitRank failed: %s", ts->err_string ? ts->err_string(rc) : "?"); }
+    CK(cudaStreamCreateWithFlags(&ts->s_comm, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ts->ev_bucket, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ts->ev_comm, cudaEventDisableTiming));
+    return W2L_OK;
+}
+
+/* one iteration of wav2lip_train.py:210-231 on the bound generator (+ frozen expert), everything on `stream` */
+int w2l_wav2lip_train_step(w2l_ctx* ctx, const float* indiv_mels, const float* x, const float* mel, const float* gt, int B, int T,
+                           float syncnet_wt, float lr, float* losses_dev, void* stream) {
+    if (!ctx || !indiv_mels || !x || !gt) return fail(W2L_EINVAL, "null argument");
+    if (B <= 0 || T <= 0) return fail(W2L_EINVAL, "bad batch B=%d T=%d", B, T);
+    if (syncnet_wt > 0.0f && (!mel || T != 5)) return fail(W2L_EINVAL, "the sync loss needs mel and T == 5 (syncnet_T)");
+    DeviceGuard g(ctx->device);
+    TrainState* ts = train_state(ctx);
+    cudaStream_t st = (cudaStream_t)stream;
+    CKR(ensure_train_scratch(ctx, B, T));
+    TrainPlan *gp, *sp = nullptr;
+    CKR(get_train_plan(ctx, W2L_NET_GENERATOR, B, T, true, false, &gp));
+    if (syncnet_wt > 0.0f) CKR(get_train_plan(ctx, W2L_NET_SYNCNET, B, T, false, true, &sp));
+    float* L = ts->loss_dev;   // [0] sync, [1] l1, [2] perceptual, [3] total
+    CK(cudaMemsetAsync(L, 0, 4 * 4, st));
+    CKR(train_forward(ctx, gp, indiv_mels, x, ts->g_buf, nullptr, 0, st));
+    const long long numel = (long long)B * 3 * T * 9216;
+    GenLossGradParams lp;
+    memset(&lp, 0, sizeof(lp));
+    if (sp) {
+        // get_sync_loss (:192-198); the scripts leave the frozen expert in train mode (:187-189): batch statistics, running
+        // averages move
+        CKR(train_forward(ctx, sp, mel, ts->g_buf, ts->a_emb, ts->v_emb, 0, st));
+        CKR(w2l_cosine_bce_loss(ctx, ts->a_emb, ts->v_emb, nullptr, B, 512, L + 0, st));
+        cosine_bce_bwd_kernel<<<(B + 3) / 4, 128, 0, st>>>(ts->a_emb, ts->v_emb, nullptr, syncnet_wt, ts->da, ts->dv, B, 512);
+        ctx->launches++;
+        CKR(train_backward(ctx, sp, ts->da, ts->dv, 0, st));
+        lp.dsync = sp->dface_in.ptr();
+    }
+    CKR(w2l_l1_loss(ctx, ts->g_buf, gt, numel, L + 1, st));
+    lp.g = ts->g_buf; lp.gt = gt; lp.dg = ts->dg_buf; lp.l1_scale = (1.0f - syncnet_wt) / (float)numel; lp.B = B; lp.T = T;
+    {
+        const int blocks = (int)std::min<long long>((numel + 255) / 256, ctx->num_sms * 16);
+        if (ctx->bf16) gen_loss_grad_kernel<true><<<blocks, 256, 0, st>>>(lp);
+        else gen_loss_grad_kernel<false><<<blocks, 256, 0, st>>>(lp);
+        ctx->launches++;
+    }
+    CKR(generator_backward_dp(ctx, gp, ts->dg_buf, st));
+    CKR(adam_step(ctx, W2L_NET_GENERATOR, lr, 0.9f, 0.999f, 1e-8f, 1.0f, st));
+    combine_losses_kernel<<<1, 32, 0, st>>>(L, syncnet_wt, 0.0f);
+    ctx->launches++;
+    if (losses_dev) CK(cudaMemcpyAsync(losses_dev, L, 4 * 4, cudaMemcpyDeviceToDevice, st));
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+/* generator output of the last fused step (B,3,T,96,96) fp32, device pointer owned by the context (tests / logging) */
+int w2l_train_last_output(w2l_ctx* ctx, float* out, int64_t n, void* stream) {
+    if (!ctx || !out || !ctx->train || !ctx->train->g_buf) return fail(W2L_ESTATE, "no fused training step has run");
+    if (n <= 0 || (size_t)n > ctx->train->g_cap) return fail(W2L_EINVAL, "bad element count");
+    DeviceGuard g(ctx->device);
+    CK(cudaMemcpyAsync(out, ctx->train->g_buf, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return W2L_OK;
+}
+
+double w2l_train_flops(w2l_ctx* ctx, int net) {
+    if (!ctx || !ctx->train || net < 0 || net > 2 || !ctx->train->last[net]) return 0.0;
+    return ctx->train->last[net]->fwd_flops;
+}
+
+/* One block, train mode, forward + backward (the operator-level entry of the per-geometry gradient tests):
+ *   y = block(x) with batch statistics; given dy: dx, dw, db, dgamma, dbeta; running stats updated in place. */
+int w2l_conv_block_train(w2l_ctx* ctx, const w2l_layer_info* spec, const float* x, int N, int H, int W, float* weight, float* bias,
+                         float* bn_weight, float* bn_bias, float* bn_mean, float* bn_var, const float* dy, float* y, float* dx,
+                         float* dw, float* db, float* dgamma, float* dbeta, void* stream) {
+    if (!ctx || !spec || !x || !weight || !y) return fail(W2L_EINVAL, "null argument");
+    if (!ctx->bf16) return fail(W2L_ESTATE, "training runs with bf16 operands: create the context with W2L_PREC_BF16");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    Layer L;
+    L.name = "block";
+    L.kind = spec->kind; L.cin = spec->cin; L.cout = spec->cout; L.kh = spec->kh; L.kw = spec->kw;
+    L.sh = spec->sh; L.sw = spec->sw; L.ph = spec->ph; L.pw = spec->pw; L.out_pad = spec->out_pad; L.residual = spec->residual != 0;
+    if (L.cout % 16 != 0) return fail(W2L_EINVAL, "cout must be a multiple of 16");
+    int Ho, Wo;
+    conv_out_dims(L, H, W, &Ho, &Wo);
+    if (Ho <= 0 || Wo <= 0) return fail(W2L_EINVAL, "empty output");
+    TrainState* ts = train_state(ctx);
+    CKR(ensure_train_scratch(ctx, 1, 1));
+    const int slot = W2L_NET_DISC;
+    std::map<std::string, ParamRef> saved;
+    saved.swap(ts->bound[slot]);
+    const long long wn = (long long)L.cin * L.cout * L.kh * L.kw;
+    ts->bound[slot]["block.conv_block.0.weight"] = ParamRef{weight, dw, wn};
+    ts->bound[slot]["block.conv_block.0.bias"] = ParamRef{bias, db, L.cout};
+    const bool bn = L.kind == W2L_BLOCK_CONV_BN_RELU || L.kind == W2L_BLOCK_CONVT_BN_RELU;
+    if (bn) {
+        ts->bound[slot]["block.conv_block.1.weight"] = ParamRef{bn_weight, dgamma, L.cout};
+        ts->bound[slot]["block.conv_block.1.bias"] = ParamRef{bn_bias, dbeta, L.cout};
+        if (bn_mean) ts->bound[slot]["block.conv_block.1.running_mean"] = ParamRef{bn_mean, nullptr, L.cout};
+        if (bn_var) ts->bound[slot]["block.conv_block.1.running_var"] = ParamRef{bn_var, nullptr, L.cout};
+    }
+    TrainPlan tp;
+    tp.net = slot; tp.N = N; tp.B = N; tp.T = 0;
+    const bool s_fold = ctx->use_fold, s_rs = ctx->use_rowstack;
+    ctx->use_fold = false; ctx->use_rowstack = false;
+    Act xin, dxin, yv, dyv, none;
+    size_t ws_need = 0;
+    int r = tp_act(&tp, &xin, N, H, W, round_up(L.cin, 16));
+    if (r == W2L_OK) r = tp_act(&tp, &dxin, N, H, W, round_up(L.cin, 16));
+    if (r == W2L_OK) r = tp_act(&tp, &yv, N, Ho, Wo, L.cout);
+    if (r == W2L_OK) r = tp_act(&tp, &dyv, N, Ho, Wo, L.cout);
+    if (r == W2L_OK) {
+        add_train_ingest(&tp, "ingest.x", 0, xin, N, L.cin, (long long)L.cin * H * W, (long long)H * W, 0, 0, W);
+        add_train_ingest(&tp, "ingest.dy", 1, dyv, N, L.cout, (long long)L.cout * Ho * Wo, (long long)Ho * Wo, 0, 0, Wo);
+        r = add_train_block(ctx, &tp, slot, 0, L, xin, yv, dyv, dx ? dxin : none, none, dw != nullptr,
+                            L.kind == W2L_BLOCK_CONVT_BN_RELU && H == 1 && W == 1, &ws_need);
+    }
+    ctx->use_fold = s_fold; ctx->use_rowstack = s_rs;
+    if (r == W2L_OK && ws_need) { void* p = nullptr; r = plan_alloc(&tp.pl, &p, ws_need); tp.wg_ws = (float*)p; }
+    if (r == W2L_OK) {
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) r = fail(W2L_ECUDA, "plan build failed: %s", cudaGetErrorString(e));
+    }
+    if (r == W2L_OK) r = repack_weights(ctx, &tp, st);
+    if (r == W2L_OK) r = launch_ingest(ctx, tp.pl.ops[tp.ingest[0]], x, st);
+    if (r == W2L_OK) r = block_forward(ctx, &tp, tp.blocks[0], true, st);
+    if (r == W2L_OK) {
+        const long long total = (long long)N * L.cout * Ho * Wo;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+        if (ctx->bf16) export_kernel<true><<<blocks, 256, 0, st>>>(yv.base, y, N, Ho, Wo, L.cout, yv.Cs, 0, 0);
+        else export_kernel<false><<<blocks, 256, 0, st>>>(yv.base, y, N, Ho, Wo, L.cout, yv.Cs, 0, 0);
+        ctx->launches++;
+    }
+    if (r == W2L_OK && dy) {
+        r = launch_ingest(ctx, tp.pl.ops[tp.ingest[1]], dy, st);
+        if (r == W2L_OK) r = block_backward(ctx, &tp, tp.blocks[0], dw != nullptr, false, st);
+        if (r == W2L_OK && dx) {
+            const long long total = (long long)N * L.cin * H * W;
+            const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+            if (ctx->bf16) export_grad_kernel<true><<<blocks, 256, 0, st>>>(dxin.ptr(), dxin.Cs, dx, N, H, W, L.cin);
+            else export_grad_kernel<false><<<blocks, 256, 0, st>>>(dxin.ptr(), dxin.Cs, dx, N, H, W, L.cin);
+            ctx->launches++;
+        }
+    }
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (r == W2L_OK && e != cudaSuccess) r = fail(W2L_ECUDA, "conv block train failed: %s", cudaGetErrorString(e));
+    free_train_plan(&tp);
+    ts->bound[slot].swap(saved);
+    return r;
 }
 
 int64_t w2l_launch_count(const w2l_ctx* ctx) { return ctx ? ctx->launches : 0; }

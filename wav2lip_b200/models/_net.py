@@ -72,15 +72,11 @@ class NativeNet(nn.Module):
         return tuple(t._version for t in ts)
 
     def _ensure(self, ref: torch.Tensor):
-        if self.training and torch.is_grad_enabled() and self._wants_grad():
-            raise NotImplementedError(
-                f"{type(self).__name__}: a differentiable training-mode forward goes through wav2lip_b200.training "
-                "(TrainStep / the autograd bridge), not through the inference plan: call .eval() and torch.no_grad() "
-                "here. (A detached result would silently drop this term's gradient.)")
         if self.training and self.NET != _lib.NET_DISC:
+            # (the mirrors' forward() routes train mode to wav2lip_b200.training before it gets here)
             raise NotImplementedError(
-                "the inference plan runs BatchNorm on its running statistics (eval mode); batch-statistics forward "
-                "+ backward live in wav2lip_b200.training: call .eval() for this entry point")
+                "this entry point runs the inference plan (BatchNorm on running statistics): call .eval(); the "
+                "train-mode forward / backward is Module.forward() in train mode (wav2lip_b200/training.py)")
         dev = self._device_index(ref)
         if self._w2l_ctx is None or self._w2l_ctx.device != dev:
             self._w2l_ctx = _lib.Context(dev, self.precision)
@@ -100,6 +96,9 @@ class NativeNet(nn.Module):
             self._w2l_ctx.load_weights(self.NET, tensors, stream)
             self._w2l_key = key
             self._w2l_range_checked = False
+            if self.precision != _lib.PREC_BF16:
+                # the flag is one per DEVICE (any context's kernels set it): start this model's check window clean
+                self._w2l_ctx.f16_overflow(clear=True, stream=stream)
         return self._w2l_ctx
 
     def _wants_grad(self) -> bool:

@@ -25,6 +25,12 @@ class Wav2Lip(NativeNet):
         self.output_block.add_module("2", nn.Sigmoid())
 
     def forward(self, audio_sequences, face_sequences):
+        if self.training:
+            # wav2lip_train.py:211,220: BatchNorm on batch statistics + an autograd node whose backward is the native
+            # dgrad / wgrad pass (wav2lip_b200/training.py, include/w2l.h w2l_train_forward / w2l_train_backward)
+            from .. import training
+            self._check_shapes(audio_sequences, face_sequences)
+            return training.train_forward(self, "gen", audio_sequences, face_sequences)
         ctx = self._ensure(face_sequences)
         self._same_device(ctx, audio_sequences, face_sequences)
         mel, face = self._in(audio_sequences), self._in(face_sequences)
@@ -45,6 +51,17 @@ class Wav2Lip(NativeNet):
         self._range_guard(ctx, stream)
         return out
 
+
+    @staticmethod
+    def _check_shapes(mel, face):
+        if face.dim() > 4:
+            B, _, T, H, W = face.shape
+            ok = tuple(mel.shape) == (B, T, 1, 80, 16) and face.shape[1] == 6 and (H, W) == (96, 96)
+        else:
+            ok = face.dim() == 4 and tuple(mel.shape) == (face.shape[0], 1, 80, 16) and tuple(face.shape[1:]) == (6, 96, 96)
+        if not ok or face.shape[0] == 0:
+            raise ValueError(f"expected (N,1,80,16)+(N,6,96,96) or (B,T,1,80,16)+(B,6,T,96,96) with N > 0, got "
+                             f"{tuple(mel.shape)} and {tuple(face.shape)}")
 
     def infer_u8(self, mel_batch, face_crops_u8):
         """The inner loop of inference.py with the batch assembly fused in (scope row f):
@@ -141,6 +158,13 @@ class Wav2Lip_disc_qual(NativeNet):
         return torch.cat([face_sequences[:, :, i] for i in range(face_sequences.size(2))], dim=0)
 
     def forward(self, face_sequences):
+        if self.training and torch.is_grad_enabled():
+            # hq_wav2lip_train.py:225-253: the perceptual loss back-propagates THROUGH the discriminator into the
+            # generator, and the discriminator's own step differentiates w.r.t. its parameters
+            from .. import training
+            if face_sequences.dim() != 5 or face_sequences.shape[1] != 3 or tuple(face_sequences.shape[3:]) != (96, 96) or face_sequences.shape[0] == 0:
+                raise ValueError(f"expected (B,3,T,96,96), got {tuple(face_sequences.shape)}")
+            return training.train_forward(self, "disc", face_sequences, None)
         ctx = self._ensure(face_sequences)
         self._same_device(ctx, face_sequences)
         x = self._in(face_sequences)
