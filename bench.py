@@ -237,6 +237,65 @@ def measure_extra(dev):
     return out
 
 
+def measure_train(dev, rank, world, steps, warmup, B=64, T=5, syncnet_wt=0.03):
+    """BASELINE configs[4]: one wav2lip_train.py:210-231 iteration per step (generator train-mode forward, get_sync_loss
+    through the frozen expert, L1, backward, gradient all-reduce over NCCL when world > 1, Adam), bf16 operands, B=64
+    windows x T=5 frames per GPU, everything native (w2l_wav2lip_train_step).  Inputs resident on the device; CUDA-event
+    timing, max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from wav2lip_b200 import _lib
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip
+    from wav2lip_b200.parallel import max_over_ranks
+    from wav2lip_b200.training import Wav2LipTrainStep, init_data_parallel
+    torch.manual_seed(0)
+    model = Wav2Lip().to(dev).train()
+    expert = SyncNet_color().to(dev).train()
+    step = Wav2LipTrainStep(model, expert, lr=1e-4, syncnet_wt=syncnet_wt)
+    if world > 1:
+        init_data_parallel(step)
+    g = torch.Generator().manual_seed(200 + rank)
+    x = torch.rand((B, 6, T, 96, 96), generator=g)
+    x[:, 0:3, :, 48:, :] = 0.0
+    indiv_mels = torch.rand((B, T, 1, 80, 16), generator=g) * 8 - 4
+    mel = torch.rand((B, 1, 80, 16), generator=g) * 8 - 4
+    gt = torch.rand((B, 3, T, 96, 96), generator=g)
+    x, indiv_mels, mel, gt = (t.to(dev) for t in (x, indiv_mels, mel, gt))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(max(3, warmup)):
+        losses = step(x, indiv_mels, mel, gt)
+    barrier()
+    ctx = step.b.ctx
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    stream = torch.cuda.current_stream(dev)
+    e0.record(stream)
+    for _ in range(steps):
+        losses = step(x, indiv_mels, mel, gt)
+    e1.record(stream)
+    torch.cuda.synchronize(dev)
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1), dev) / steps
+    launches = (ctx.launch_count() - l0) // steps
+    gen_f = ctx.lib.w2l_train_flops(ctx.h, _lib.NET_GENERATOR)
+    syn_f = ctx.lib.w2l_train_flops(ctx.h, _lib.NET_SYNCNET)
+    flop = 3.0 * gen_f + 2.0 * syn_f       # forward + dgrad + wgrad of the generator; forward + dgrad of the frozen expert
+    lv = [float(v) for v in losses.cpu()]
+    n_param = sum(p.numel() for p in model.parameters())
+    return {"config": f"wav2lip_train.py step (gen + L1 + sync loss {syncnet_wt}), bf16 operands / fp32 master+grads, B={B} x T={T} per GPU, "
+                      f"{world} GPU(s), gradient all-reduce {'ncclAllReduce(avg) in 3 buckets overlapped with the backward' if world > 1 else 'n/a (1 GPU)'}",
+            "ms_per_step": ms, "crops_per_s": world * B * T / ms * 1e3, "windows_per_s": world * B / ms * 1e3,
+            "algorithmic_tflop_per_step_per_gpu": flop / 1e12, "tflops_per_gpu": flop / ms / 1e9,
+            "kernel_launches_per_step": int(launches), "allreduce_bytes_per_step": int(4 * n_param) if world > 1 else 0,
+            "losses_last_step": {"sync": lv[0], "l1": lv[1], "total": lv[3]}}
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port; the reference is
     Python and cannot travel to the GPU box) on all host cores, bounded sample per step."""
@@ -285,6 +344,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the SyncNet / disc / mel side measurements")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table to this file")
+    ap.add_argument("--workload", default="infer", choices=["infer", "train"],
+                    help="infer: the headline metric (default).  train: BASELINE configs[4], one training iteration per step")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -313,6 +374,20 @@ def main():
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):
             os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=dev)
+    if args.workload == "train":
+        tb = 64 if args.batch == B_DEFAULT else args.batch
+        r = measure_train(dev, rank, world, args.steps, args.warmup, B=tb, T=args.frames)
+        if rank == 0:
+            line = {"metric": "wav2lip_train.py iterations: 96x96 face-crops/sec trained (B=64/GPU, T=5, bf16)", "value": r["crops_per_s"],
+                    "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": {"workload": r["config"], "per_gpu_batch": tb * args.frames, "global_batch": tb * args.frames * world,
+                               "parallelism": f"dp{world}", "l2": "activations of one step (~10 GB) >> L2"},
+                    "gpu_launches": r["kernel_launches_per_step"] * args.steps, "train": r}
+            print(json.dumps(line), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
     B, T = args.batch, args.frames
     N = B * T
 
@@ -454,6 +529,10 @@ def main():
     extra = None
     if rank == 0 and world == 1 and not args.no_extra:
         extra = measure_extra(dev)
+        try:
+            extra["train_step"] = measure_train(dev, 0, 1, steps=5, warmup=3)
+        except Exception as e:  # the training row must not take the headline line down
+            extra["train_step"] = {"error": repr(e)[:300]}
 
     # ---- CPU baseline (rank 0, N=1 only) ----
     cpu = None

@@ -121,6 +121,22 @@ int w2l_generator_forward_u8(w2l_ctx* ctx, const float* mel_dev, const uint8_t* 
 int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_host, const uint8_t* faces_host,
                                   uint8_t* out_host, int N);
 
+/* Scope row (f2), the rest of the batch assembly: the two cv2.resize calls and the paste-back of inference.py, bit-identical
+ * to OpenCV's fixed-point 8-bit INTER_LINEAR (11-bit coefficients; restated and pinned against cv2 in oracle/pipeline_oracle.py).
+ *   frames (F,H,W,3) uint8 BGR on the device; boxes_host: N rows (frame index, y1, y2, x1, x2) in HOST memory (validated).
+ *   w2l_crop_resize_u8    replaces `cv2.resize(face, (96, 96))` of every frames[f][y1:y2, x1:x2] (inference.py:102,:126)
+ *                         -> crops (N,96,96,3) uint8, the input of w2l_generator_forward_u8.
+ *   w2l_paste_u8          replaces `p = cv2.resize(p.astype(np.uint8), (x2-x1, y2-y1)); f[y1:y2, x1:x2] = p` on a copy of the
+ *                         frame (inference.py:123, :267-271): pred (N,96,96,3) uint8 -> out_frames (N,H,W,3) uint8.
+ *   w2l_lipsync_frames_u8 the whole inner loop of inference.py:120-140 + :259-271 in one call: crop + resize -> mask / concat
+ *                         / 255 -> generator -> x255 -> uint8 -> resize -> paste.  mel (N,1,80,16) fp32. */
+int w2l_crop_resize_u8(w2l_ctx* ctx, const uint8_t* frames_dev, int F, int H, int W, const int32_t* boxes_host, int N,
+                       uint8_t* crops_dev, void* stream);
+int w2l_paste_u8(w2l_ctx* ctx, const uint8_t* pred_dev, const uint8_t* frames_dev, int F, int H, int W,
+                 const int32_t* boxes_host, int N, uint8_t* out_frames_dev, void* stream);
+int w2l_lipsync_frames_u8(w2l_ctx* ctx, const float* mel_dev, const uint8_t* frames_dev, int F, int H, int W,
+                          const int32_t* boxes_host, int N, uint8_t* out_frames_dev, void* stream);
+
 /* Replaces `SyncNet_color.forward(audio, face)` (syncnet.py:55-66):
  *   mel (B,1,80,16), face (B,15,48,96) -> audio_emb (B,512), face_emb (B,512), both L2-normalised. */
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel_dev, const float* face_dev,

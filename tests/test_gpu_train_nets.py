@@ -1,0 +1,279 @@
+"""Training row, network level, through the public surface: the mirrors in train mode + autograd
+(the reference scripts' `loss.backward()`), and the fused native step `Wav2LipTrainStep` (w2l_wav2lip_train_step).
+
+What can be asserted, and why (tests/test_precision_model.py): on the reference's initialisation the
+generator's end-to-end gradients amplify relative perturbations by ~1e5 (fp32 vs fp64: 0.6 %; TF32-class operands, i.e.
+the reference's own GPU arithmetic: 24 %; two bf16 runs whose inputs differ by 1e-7: 50 %, cosine 0.87) — ReLU-mask flips
+of near-zero pre-activations under batch-statistics BatchNorm.  So:
+  * kernels are held to the per-block bar in tests/test_gpu_train_blocks.py (2e-2, every geometry);
+  * the WIRING of the networks (skip-concat gradient split, residual and skip accumulation, transposed-conv phases, the
+    expert's and the discriminator's input gradients, t-major flatten) is checked here on weights whose BatchNorm shift
+    keeps every ReLU active (beta = 4: the backward is then smooth and bf16 rounding stays at the per-cent level), against
+    float64 autograd through the oracle, every parameter tensor;
+  * the reference's own step (tests/golden/train.npz, produced by the real modules + torch.optim.Adam) pins what IS well
+    conditioned: losses, the generator output, the head's gradient, the Adam update size, the BatchNorm buffers."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import loss_oracle as LO
+from oracle import w2l_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel_l2(got, ref):
+    return ((got.double().cpu() - ref.double()).norm() / (ref.double().norm() + 1e-30)).item()
+
+
+def fp3(t):
+    f = t.detach().double().flatten().cpu()
+    return np.array([f.sum().item(), f.abs().sum().item(), f.abs().max().item()])
+
+
+def relu_active(sd, beta=4.0):
+    return {k: (torch.full_like(v, beta) if k.endswith("conv_block.1.bias") else v.clone()) for k, v in sd.items()}
+
+
+def autograd_reference(forward, sd, scalar_of_outputs):
+    """float64 autograd through the oracle: returns {param name: grad} for every weight / bias."""
+    leaves = {k: v.double().clone().requires_grad_(k.endswith(".weight") or k.endswith(".bias"))
+              for k, v in sd.items() if v.dtype.is_floating_point}
+    out = forward(leaves)
+    loss = scalar_of_outputs(out)
+    names = [k for k, v in leaves.items() if v.requires_grad]
+    return out, dict(zip(names, torch.autograd.grad(loss, [leaves[k] for k in names], allow_unused=True)))
+
+
+def check_param_grads(module, ref, tol, skip_suffix="conv_block.0.bias"):
+    scale = max(g.double().norm().item() for g in ref.values() if g is not None)
+    worst = 0.0
+    for name, p in module.named_parameters():
+        r = ref[name]
+        if name.endswith(skip_suffix) and "conv_block.1" not in name and module.NET != 2:
+            continue                      # conv bias under a BatchNorm: the true gradient is 0 (we return exactly 0)
+        if r is None or r.double().norm().item() < 1e-6 * scale:
+            continue                      # structurally zero gradients (a constant shift removed by the next BatchNorm)
+        assert p.grad is not None, name
+        e = rel_l2(p.grad, r)
+        worst = max(worst, e)
+        assert e <= tol, (name, e)
+    return worst
+
+
+def _train_inputs(B, seed):
+    g = torch.Generator().manual_seed(seed)
+    indiv_mels, x = O.make_generator_inputs(B, seed=seed, t=5)
+    mel = torch.rand((B, 1, 80, 16), generator=g) * 8 - 4
+    gt = torch.rand((B, 3, 5, 96, 96), generator=g)
+    return x, indiv_mels, mel, gt
+
+
+def test_generator_train_mode_forward_matches_oracle():
+    """model.train(); model(indiv_mels, x): BatchNorm on batch statistics over the T*B flatten, running averages and
+    num_batches_tracked updated as nn.BatchNorm2d does."""
+    from wav2lip_b200.models import Wav2Lip
+    sd = O.make_state_dict("generator", 0, init="default")
+    mel, face = O.make_generator_inputs(2, seed=7, t=5)
+    ref_sd = {k: v.clone() for k, v in sd.items()}
+    with torch.no_grad():
+        ref = O.generator_forward(ref_sd, mel, face, training=True)
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().train()
+    with torch.no_grad():
+        y = g(mel.cuda(), face.cuda())
+    assert tuple(y.shape) == (2, 3, 5, 96, 96)
+    err = (y.cpu() - ref).abs().max().item()
+    assert err <= 1e-2, err                       # bf16 operands (8-bit mantissa) through 50 blocks; measured ~2e-3
+    assert (y.cpu() - ref).abs().mean().item() <= 1e-3
+    got = g.state_dict()
+    for k, v in ref_sd.items():
+        if k.endswith("running_mean"):
+            assert (got[k].cpu() - v).abs().max().item() <= 2e-2 * max(1.0, v.abs().max().item()), k
+        elif k.endswith("running_var"):
+            assert rel_l2(got[k], v) <= 3e-2, k
+        elif k.endswith("num_batches_tracked"):
+            assert int(got[k]) == 1, k
+
+
+def test_generator_backward_wiring_against_float64_autograd():
+    """Every parameter gradient of the generator (4-D call) through the autograd bridge, all ReLUs active."""
+    from wav2lip_b200.models import Wav2Lip
+    sd = relu_active(O.make_state_dict("generator", 0, init="default"))
+    N = 4
+    mel, face = O.make_generator_inputs(N, seed=1)
+    dout = torch.randn((N, 3, 96, 96), generator=torch.Generator().manual_seed(4)) / (N * 3 * 9216)
+    out_ref, ref = autograd_reference(lambda s: O.generator_forward(s, mel.double(), face.double(), training=True), sd,
+                                      lambda o: (o * dout.double()).sum())
+    g = Wav2Lip()
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda().train()
+    y = g(mel.cuda(), face.cuda())
+    assert y.requires_grad
+    assert (y.detach().cpu() - out_ref.detach()).abs().max().item() <= 1e-2
+    (y * dout.cuda()).sum().backward()
+    worst = check_param_grads(g, ref, 0.12)       # measured: median 2.5 %, the bf16 rounding of ~50 blocks
+    assert rel_l2(g.output_block[1].weight.grad, ref["output_block.1.weight"]) <= 3e-2
+    assert worst > 0.0
+
+
+def test_generator_backward_5d_is_the_tmajor_flatten():
+    """wav2lip.py:93-94,119-120 in the backward: a 5-D training call equals the 4-D call on the t-major flattened batch."""
+    from wav2lip_b200.models import Wav2Lip
+    sd = relu_active(O.make_state_dict("generator", 0, init="default"))
+    mel5, face5 = O.make_generator_inputs(2, seed=3, t=3)
+    mel4 = torch.cat([mel5[:, i] for i in range(3)], 0)
+    face4 = torch.cat([face5[:, :, i] for i in range(3)], 0)
+    d5 = torch.randn((2, 3, 3, 96, 96), generator=torch.Generator().manual_seed(5))
+    d4 = torch.cat([d5[:, :, i] for i in range(3)], 0)
+    grads = []
+    for mel, face, d in ((mel5, face5, d5), (mel4, face4, d4)):
+        g = Wav2Lip()
+        g.load_state_dict(sd, strict=True)
+        g = g.cuda().train()
+        y = g(mel.cuda(), face.cuda())
+        (y * d.cuda()).sum().backward()
+        grads.append({n: p.grad.clone() for n, p in g.named_parameters()})
+    for n in grads[0]:
+        assert torch.equal(grads[0][n], grads[1][n]), n
+
+
+def test_syncnet_training_through_autograd_bridge():
+    """color_syncnet_train.py:146-163: a, v = model(mel, x); loss = cosine_loss(a, v, y); loss.backward() — both encoders,
+    every parameter, against float64 autograd (all ReLUs active)."""
+    from wav2lip_b200.models import SyncNet_color
+    sd = relu_active(O.make_state_dict("syncnet", 2, init="default"))
+    mel, face = O.make_syncnet_inputs(4, seed=5)
+    y = torch.tensor([[1.0], [0.0], [1.0], [0.0]])
+
+    def loss_of(av):
+        d = F.cosine_similarity(av[0], av[1])
+        return F.binary_cross_entropy(d.unsqueeze(1), y.to(d.dtype))
+
+    (a_ref, v_ref), ref = autograd_reference(lambda s: O.syncnet_forward(s, mel.double(), face.double(), training=True), sd, loss_of)
+    s = SyncNet_color()
+    s.load_state_dict(sd, strict=True)
+    s = s.cuda().train()
+    a, v = s(mel.cuda(), face.cuda())
+    assert (a.detach().cpu() - a_ref.detach()).abs().max().item() <= 5e-3
+    assert (v.detach().cpu() - v_ref.detach()).abs().max().item() <= 5e-3
+    d = F.cosine_similarity(a, v)
+    loss = F.binary_cross_entropy(d.unsqueeze(1), y.cuda())
+    loss.backward()
+    check_param_grads(s, ref, 0.12)
+
+
+def test_sync_loss_gradient_reaches_the_generator_output():
+    """get_sync_loss (wav2lip_train.py:192-198) with the frozen expert in train mode: dL/dg through the slice + channel
+    stack (torch ops) and the expert's input gradient (native), against float64 autograd."""
+    from wav2lip_b200.models import SyncNet_color
+    sd = relu_active(O.make_state_dict("syncnet", 1, init="default"))
+    B = 3
+    gen = torch.Generator().manual_seed(11)
+    mel = torch.rand((B, 1, 80, 16), generator=gen) * 8 - 4
+    g0 = torch.rand((B, 3, 5, 96, 96), generator=gen)
+    g64 = g0.double().requires_grad_(True)
+    a, v = O.syncnet_forward({k: t.double() for k, t in sd.items() if t.dtype.is_floating_point}, mel.double(),
+                             LO.stack_lower_halves(g64), training=True)
+    LO.cosine_loss(a, v, torch.ones(B, 1, dtype=torch.float64)).backward()
+    s = SyncNet_color()
+    s.load_state_dict(sd, strict=True)
+    s = s.cuda().train()
+    for p in s.parameters():
+        p.requires_grad_(False)                                   # wav2lip_train.py:188-189
+    gg = g0.cuda().requires_grad_(True)
+    half = gg[:, :, :, gg.size(3) // 2:]
+    stacked = torch.cat([half[:, :, i] for i in range(5)], dim=1)  # :193-194, torch ops, as the script does
+    a2, v2 = s(mel.cuda(), stacked)
+    d = F.cosine_similarity(a2, v2)
+    F.binary_cross_entropy(d.unsqueeze(1), torch.ones(B, 1).cuda()).backward()
+    assert gg.grad is not None and gg.grad[:, :, :, :48].abs().max().item() == 0.0
+    assert rel_l2(gg.grad, g64.grad) <= 0.12
+    assert all(p.grad is None for p in s.parameters())
+
+
+def test_disc_training_through_autograd_bridge():
+    """hq_wav2lip_train.py:245-253: BCE(disc(gt), 1) + BCE(disc(g.detach()), 0), two backward() calls accumulating."""
+    from wav2lip_b200.models import Wav2Lip_disc_qual
+    sd = O.make_state_dict("disc", 3, init="default")
+    real = O.make_disc_inputs(2, 5, 0)
+    fake = O.make_disc_inputs(2, 5, 1)
+
+    def loss_of(_):
+        return None
+
+    leaves = {k: v.double().clone().requires_grad_(True) for k, v in sd.items() if v.dtype.is_floating_point}
+    pr = O.disc_forward(leaves, real.double())
+    pf = O.disc_forward(leaves, fake.double())
+    lref = F.binary_cross_entropy(pr, torch.ones_like(pr)) + F.binary_cross_entropy(pf, torch.zeros_like(pf))
+    names = list(leaves.keys())
+    ref = dict(zip(names, torch.autograd.grad(lref, [leaves[k] for k in names])))
+    d = Wav2Lip_disc_qual()
+    d.load_state_dict(sd, strict=True)
+    d = d.cuda().train()
+    p1 = d(real.cuda())
+    F.binary_cross_entropy(p1, torch.ones_like(p1)).backward()
+    p2 = d(fake.cuda())
+    F.binary_cross_entropy(p2, torch.zeros_like(p2)).backward()
+    assert (p1.detach().cpu() - pr.detach()).abs().max().item() <= 5e-3
+    for n, p in d.named_parameters():
+        assert rel_l2(p.grad, ref[n]) <= 0.15, (n, rel_l2(p.grad, ref[n]))   # LeakyReLU slope flips, no BatchNorm
+
+
+def test_fused_train_step_against_the_reference_golden(golden_dir):
+    """Two iterations of wav2lip_train.py:210-231 as native calls (B=2, T=5, syncnet_wt 0.03, lr 1e-4) against the REAL
+    reference + torch.optim.Adam (tests/golden/train.npz)."""
+    from wav2lip_b200.models import SyncNet_color, Wav2Lip
+    from wav2lip_b200.training import Wav2LipTrainStep
+    gold = np.load(os.path.join(golden_dir, "train.npz"))
+    gen = Wav2Lip()
+    gen.load_state_dict(O.make_state_dict("generator", 0, init="default"), strict=True)
+    gen = gen.cuda().train()
+    expert = SyncNet_color()
+    expert.load_state_dict(O.make_state_dict("syncnet", 1, init="default"), strict=True)
+    expert = expert.cuda().train()
+    before = {k: v.clone() for k, v in gen.state_dict().items()}
+    x, indiv_mels, mel, gt = _train_inputs(2, seed=7)
+    step = Wav2LipTrainStep(gen, expert, lr=1e-4, syncnet_wt=0.03)
+    for it in range(2):
+        losses = step(x.cuda(), indiv_mels.cuda(), mel.cuda(), gt.cuda()).cpu().numpy()   # [sync, l1, 0, total]
+        ref = gold[f"gen{it}_losses"]                                                   # [loss, sync, l1]
+        assert abs(losses[1] - ref[2]) <= 2e-3 * ref[2], (it, losses, ref)              # L1: mean over 276 k values
+        assert abs(losses[0] - ref[1]) <= 3e-2 * ref[1], (it, losses, ref)              # sync: cosine of bf16 embeddings
+        assert abs(losses[3] - ref[0]) <= 5e-3 * ref[0], (it, losses, ref)
+        gfp = fp3(step.last_output(2, 5))
+        assert abs(gfp[1] - gold[f"gen{it}_g_fp"][1]) <= 2e-3 * gold[f"gen{it}_g_fp"][1]
+        if it == 0:
+            # the head's gradient sees no amplification: it matches the reference's
+            hw = step.b.grads["output_block.1.weight"].flatten().cpu().numpy()
+            ref_hw = gold["gen0_grad_head_w"]
+            assert np.linalg.norm(hw - ref_hw) <= 5e-2 * np.linalg.norm(ref_hw)
+            # first Adam step: every weight with a non-negligible gradient moves by lr
+            after = gen.state_dict()
+            k = "output_block.1.weight"
+            dlt = (after[k] - before[k]).abs().flatten().cpu()
+            big = torch.from_numpy(np.abs(ref_hw) > 1e-6)
+            assert torch.allclose(dlt[big], torch.full_like(dlt[big], 1e-4), rtol=2e-2)
+            moved = sum(int(((after[n] - before[n]).abs() > 0.5e-4).sum()) for n in after if n.endswith("conv_block.0.weight"))
+            total = sum(after[n].numel() for n in after if n.endswith("conv_block.0.weight"))
+            assert moved >= 0.98 * total
+        # parameters and BatchNorm buffers after the step: abs-sum fingerprints of all 352 tensors
+        names = list(gold[f"gen{it}_sd_names"])
+        sd_now = gen.state_dict()
+        assert names == list(sd_now.keys())
+        got = np.stack([fp3(sd_now[n]) for n in names])
+        ref_fp = gold[f"gen{it}_sd_fp"]
+        is_stat = np.array(["running" in n for n in names])
+        is_cnt = np.array(["num_batches" in n for n in names])
+        rel = np.abs(got[:, 1] - ref_fp[:, 1]) / np.maximum(ref_fp[:, 1], 1e-12)
+        assert np.all(rel[is_cnt] == 0)
+        assert np.all(rel[is_stat & ~is_cnt] <= 3e-2), rel[is_stat & ~is_cnt].max()
+        assert np.all(rel[~is_stat & ~is_cnt] <= 2e-3), rel[~is_stat & ~is_cnt].max()
+        # the frozen expert ran in train mode (the scripts' quirk): its running averages moved, its weights did not
+        ex = np.stack([fp3(v) for k, v in expert.state_dict().items() if "running" in k or "num_batches" in k])
+        rel_e = np.abs(ex[:, 1] - gold[f"gen{it}_expert_buf_fp"][:, 1]) / np.maximum(gold[f"gen{it}_expert_buf_fp"][:, 1], 1e-12)
+        assert rel_e.max() <= 3e-2, rel_e.max()

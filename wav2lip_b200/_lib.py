@@ -29,6 +29,7 @@ EXPORTS = [
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
     "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
     "w2l_f16_overflow",
+    "w2l_crop_resize_u8", "w2l_paste_u8", "w2l_lipsync_frames_u8",
     "w2l_train_bind", "w2l_train_forward", "w2l_train_backward", "w2l_adam_step", "w2l_wav2lip_train_step",
     "w2l_train_last_output", "w2l_train_flops", "w2l_comm_unique_id", "w2l_comm_init", "w2l_conv_block_train",
 ]
@@ -99,6 +100,9 @@ def get_lib() -> C.CDLL:
     lib.w2l_profile_plan.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.w2l_f16_overflow.argtypes = [vp, i32, C.POINTER(i32), vp]
     f32 = C.c_float
+    lib.w2l_crop_resize_u8.argtypes = [vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
+    lib.w2l_paste_u8.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
+    lib.w2l_lipsync_frames_u8.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
     lib.w2l_train_bind.argtypes = [vp, i32, i32, C.POINTER(cp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     lib.w2l_train_forward.argtypes = [vp, i32, vp, vp, vp, vp, i32, i32, i32, vp]
     lib.w2l_train_backward.argtypes = [vp, i32, vp, vp, vp, i32, vp]

@@ -25,6 +25,7 @@
 #include "convt_fused.cuh"
 #include "mel.cuh"
 #include "netspec.h"
+#include "resize.cuh"
 #include "train_kernels.cuh"
 #include "wgrad_tcgen05.cuh"
 
@@ -150,6 +151,9 @@ int w2l_destroy(w2l_ctx* ctx) {
     if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
     for (int i = 0; i < 2; ++i) { if (ctx->ev_in[i]) cudaEventDestroy(ctx->ev_in[i]); if (ctx->ev_done[i]) cudaEventDestroy(ctx->ev_done[i]); if (ctx->ev_out[i]) cudaEventDestroy(ctx->ev_out[i]); }
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->boxes_dev) cudaFree(ctx->boxes_dev);
+    if (ctx->crops_dev) cudaFree(ctx->crops_dev);
+    if (ctx->preds_dev) cudaFree(ctx->preds_dev);
     if (ctx->mel_tw) cudaFree(ctx->mel_tw);
     if (ctx->mel_bvals) cudaFree(ctx->mel_bvals);
     if (ctx->mel_boff) cudaFree(ctx->mel_boff);
@@ -334,6 +338,78 @@ int w2l_generator_forward_u8_host(w2l_ctx* ctx, const float* mel_h, const uint8_
                         out_h + b0 * per_out, bc * per_out, true));
     }
     return host_drain(ctx, 0);
+}
+
+
+// ---- scope row f2: the two cv2.resize calls and the paste around the generator call (inference.py:126, :269-271) ----
+static int upload_boxes(w2l_ctx* ctx, const int32_t* boxes, int N, int F, int H, int W, cudaStream_t st) {
+    for (int n = 0; n < N; ++n) {
+        const int32_t* b = boxes + 5 * n;
+        if (b[0] < 0 || b[0] >= F || b[1] < 0 || b[2] > H || b[1] >= b[2] || b[3] < 0 || b[4] > W || b[3] >= b[4])
+            return fail(W2L_EINVAL, "box %d = (frame %d, y %d:%d, x %d:%d) is empty or outside the %d frames of %dx%d", n, b[0], b[1], b[2], b[3], b[4], F, H, W);
+    }
+    if (ctx->box_cap < N) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->boxes_dev) cudaFree(ctx->boxes_dev);
+        void* p = nullptr;
+        CKR(dev_alloc(&p, (size_t)N * 5 * 4));
+        ctx->boxes_dev = (int*)p; ctx->box_cap = N;
+    }
+    CK(cudaMemcpyAsync(ctx->boxes_dev, boxes, (size_t)N * 5 * 4, cudaMemcpyHostToDevice, st));
+    return W2L_OK;
+}
+
+int w2l_crop_resize_u8(w2l_ctx* ctx, const uint8_t* frames, int F, int H, int W, const int32_t* boxes_host, int N, uint8_t* crops,
+                       void* stream) {
+    if (!ctx || !frames || !boxes_host || !crops) return fail(W2L_EINVAL, "null argument");
+    if (F <= 0 || H <= 0 || W <= 0 || N <= 0) return fail(W2L_EINVAL, "bad shape");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CKR(upload_boxes(ctx, boxes_host, N, F, H, W, st));
+    const long long total = (long long)N * 96 * 96;
+    crop_resize_kernel<<<(int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16), 256, 0, st>>>(frames, H, W, ctx->boxes_dev, N, 96, crops);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int w2l_paste_u8(w2l_ctx* ctx, const uint8_t* pred, const uint8_t* frames, int F, int H, int W, const int32_t* boxes_host, int N,
+                 uint8_t* out_frames, void* stream) {
+    if (!ctx || !pred || !frames || !boxes_host || !out_frames) return fail(W2L_EINVAL, "null argument");
+    if (F <= 0 || H <= 0 || W <= 0 || N <= 0) return fail(W2L_EINVAL, "bad shape");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    CKR(upload_boxes(ctx, boxes_host, N, F, H, W, st));
+    const long long total = (long long)N * H * W;
+    paste_kernel<<<(int)std::min<long long>((total + 255) / 256, ctx->num_sms * 32), 256, 0, st>>>(pred, 96, frames, H, W, ctx->boxes_dev, N, out_frames);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
+}
+
+int w2l_lipsync_frames_u8(w2l_ctx* ctx, const float* mel, const uint8_t* frames, int F, int H, int W, const int32_t* boxes_host, int N,
+                          uint8_t* out_frames, void* stream) {
+    if (!ctx || !mel || !frames || !boxes_host || !out_frames) return fail(W2L_EINVAL, "null argument");
+    if (F <= 0 || H <= 0 || W <= 0 || N <= 0) return fail(W2L_EINVAL, "bad shape");
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t cb = (size_t)N * 96 * 96 * 3;
+    if (ctx->crop_cap < cb) {
+        CK(cudaDeviceSynchronize());
+        if (ctx->crops_dev) cudaFree(ctx->crops_dev);
+        if (ctx->preds_dev) cudaFree(ctx->preds_dev);
+        void* p = nullptr;
+        CKR(dev_alloc(&p, cb)); ctx->crops_dev = (uint8_t*)p;
+        CKR(dev_alloc(&p, cb)); ctx->preds_dev = (uint8_t*)p;
+        ctx->crop_cap = cb;
+    }
+    CKR(w2l_crop_resize_u8(ctx, frames, F, H, W, boxes_host, N, ctx->crops_dev, stream));
+    CKR(w2l_generator_forward_u8(ctx, mel, ctx->crops_dev, ctx->preds_dev, N, stream));
+    const long long total = (long long)N * H * W;
+    paste_kernel<<<(int)std::min<long long>((total + 255) / 256, ctx->num_sms * 32), 256, 0, st>>>(ctx->preds_dev, 96, frames, H, W, ctx->boxes_dev, N, out_frames);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return W2L_OK;
 }
 
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float* a_emb, float* v_emb, int B, void* stream) {

@@ -86,6 +86,71 @@ class Wav2Lip(NativeNet):
         return out
 
 
+    @staticmethod
+    def _boxes(boxes, n_expected=None):
+        import numpy as np
+        b = np.ascontiguousarray(np.asarray(boxes.cpu() if isinstance(boxes, torch.Tensor) else boxes, dtype=np.int32))
+        if b.ndim != 2 or b.shape[1] != 5 or (n_expected is not None and b.shape[0] != n_expected):
+            raise ValueError(f"expected boxes of shape (N,5) = (frame index, y1, y2, x1, x2), got {b.shape}")
+        return b
+
+    def crop_resize(self, frames_u8, boxes):
+        """inference.py:102 + :126 on the GPU: frames (F,H,W,3) uint8 BGR (CUDA), boxes (N,5) rows (frame index, y1, y2, x1, x2)
+        -> (N,96,96,3) uint8, bit-identical to `cv2.resize(frames[f][y1:y2, x1:x2], (96, 96))`."""
+        ctx = self._ensure(frames_u8)
+        self._same_device(ctx, frames_u8)
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
+            raise ValueError(f"expected uint8 (F,H,W,3) frames, got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+        b = self._boxes(boxes)
+        fr = frames_u8.contiguous()
+        out = torch.empty((b.shape[0], 96, 96, 3), device=fr.device, dtype=torch.uint8)
+        if b.shape[0] == 0:
+            return out
+        stream = torch.cuda.current_stream(fr.device).cuda_stream
+        _lib.check(ctx.lib.w2l_crop_resize_u8(ctx.h, self._p(fr), fr.shape[0], fr.shape[1], fr.shape[2],
+                                              b.ctypes.data_as(C.POINTER(C.c_int32)), b.shape[0], self._p(out), C.c_void_p(stream)))
+        return out
+
+    def paste(self, pred_u8, frames_u8, boxes):
+        """inference.py:267-271 on the GPU: pred (N,96,96,3) uint8 -> (N,H,W,3) uint8 = copies of frames[box.frame] with the
+        prediction resized to the box (cv2.resize arithmetic, bit-identical) and pasted."""
+        ctx = self._ensure(frames_u8)
+        self._same_device(ctx, frames_u8, pred_u8)
+        b = self._boxes(boxes, pred_u8.shape[0])
+        if pred_u8.dtype != torch.uint8 or tuple(pred_u8.shape[1:]) != (96, 96, 3) or frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4:
+            raise ValueError("expected uint8 pred (N,96,96,3) and uint8 frames (F,H,W,3)")
+        fr, pr = frames_u8.contiguous(), pred_u8.contiguous()
+        out = torch.empty((b.shape[0],) + tuple(fr.shape[1:]), device=fr.device, dtype=torch.uint8)
+        if b.shape[0] == 0:
+            return out
+        stream = torch.cuda.current_stream(fr.device).cuda_stream
+        _lib.check(ctx.lib.w2l_paste_u8(ctx.h, self._p(pr), self._p(fr), fr.shape[0], fr.shape[1], fr.shape[2],
+                                        b.ctypes.data_as(C.POINTER(C.c_int32)), b.shape[0], self._p(out), C.c_void_p(stream)))
+        return out
+
+    def infer_frames(self, mel_batch, frames_u8, boxes):
+        """The whole inner loop of inference.py (:120-140, :259-271) in one native call: for every (mel chunk, box) pair crop the
+        face box out of its frame, resize to 96x96, mask / concat / normalise, run the generator, scale to uint8, resize the
+        prediction back to the box and paste it into a copy of the frame.
+        mel_batch (N,1,80,16) float, frames (F,H,W,3) uint8 BGR, boxes (N,5) rows (frame index, y1, y2, x1, x2) -> (N,H,W,3) uint8."""
+        ctx = self._ensure(frames_u8)
+        self._same_device(ctx, frames_u8, mel_batch)
+        b = self._boxes(boxes, mel_batch.shape[0])
+        if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[3] != 3:
+            raise ValueError(f"expected uint8 (F,H,W,3) frames, got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+        mel = self._in(mel_batch)
+        if tuple(mel.shape) != (b.shape[0], 1, 80, 16):
+            raise ValueError(f"expected mel (N,1,80,16), got {tuple(mel.shape)}")
+        fr = frames_u8.contiguous()
+        out = torch.empty((b.shape[0],) + tuple(fr.shape[1:]), device=fr.device, dtype=torch.uint8)
+        if b.shape[0] == 0:
+            return out
+        stream = torch.cuda.current_stream(fr.device).cuda_stream
+        _lib.check(ctx.lib.w2l_lipsync_frames_u8(ctx.h, self._p(mel), self._p(fr), fr.shape[0], fr.shape[1], fr.shape[2],
+                                                 b.ctypes.data_as(C.POINTER(C.c_int32)), b.shape[0], self._p(out), C.c_void_p(stream)))
+        self._range_guard(ctx, stream)
+        return out
+
     def infer_stream(self, batches, device=None):
         """Serving loop over HOST batches with the copies overlapped with the kernels (w2l_generator_submit_*_host /
         w2l_host_wait, include/w2l.h): `batches` yields (mel, faces) CPU tensors — fp32 (N,1,80,16) with either fp32
