@@ -176,6 +176,7 @@ struct w2l_ctx {
     bool use_fold = true;   // W2L_DISABLE_FOLD=1 / driver rejects overlapping-stride tensor maps
     bool use_pdl = true;      // W2L_DISABLE_PDL=1
     bool use_rowstack = true;  // W2L_DISABLE_ROWSTACK=1
+    bool use_mel_v2 = true;    // W2L_DISABLE_MELV2=1
     NetW nets[3];
     std::map<std::string, std::unique_ptr<Plan>> plans;
     Plan* last_plan[3] = {nullptr, nullptr, nullptr};

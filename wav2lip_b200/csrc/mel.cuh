@@ -19,6 +19,8 @@
 
 #include <stdint.h>
 
+#include "mel_consts.h"
+
 namespace w2l {
 
 constexpr int MEL_FPB = 4;
@@ -182,5 +184,169 @@ __global__ void __launch_bounds__(MEL_FPB* MEL_TPF) mel_kernel(const MelParams p
 }
 
 constexpr int kMelSmemBytes = MEL_TW_TOTAL * 16 + MEL_FPB * 800 * 16 + MEL_FPB * 404 * 4 + MEL_BANDS * MEL_FPB * 4;
+
+// ------------------------------------------------------------------------------------------------
+// mel_kernel_v2 — the same arithmetic with the 400-point FFT held in REGISTERS (round 2).
+//
+// The first version round-tripped double2 data through shared memory on every Stockham pass and was shared-memory bound
+// (ncu: l1tex 85 %, 0.026 of the HBM roof).  Here 400 = 25 x 16 is split Cooley-Tukey style across threads:
+//   step 1  (25 threads per frame, thread = n1): the 16 packed samples z[n1 + 25 n2] are gathered straight from HBM/L1
+//           (coalesced across n1), pre-emphasised, windowed (Hann from two table values per thread and compile-time
+//           (cos, sin)(n2 pi/8) constants) and transformed by a 16-point FFT (4 x 4) entirely in registers; the result is
+//           multiplied by W400^(n1 k2) (a 15-step recurrence from one table value) and written ONCE to shared memory;
+//   step 3  (16 threads per frame, thread = k2): 25-point FFT (5 x 5) in registers over n1, then the real-FFT split
+//           X[k] = E[k] + W800^k O[k], whose partner Z[400 - k] lives in thread 16 - k2 of the same 16-lane group:
+//           warp shuffles, no second shared-memory pass; |X| goes to shared memory as fp32 for the sparse mel product.
+// Shared-memory traffic per frame drops from ~70 KB to ~18 KB; all twiddles inside the small FFTs are compile-time
+// constants (mel_consts.h).  Same dtypes as before: float64 up to the complex64 rounding of the spectrum, fp32 after.
+// ------------------------------------------------------------------------------------------------
+constexpr int MEL2_FPB = 5;        // frames per block: 125 of 128 threads busy in step 1, 80 in step 3
+constexpr int MEL2_THREADS = 128;
+constexpr int kMel2SmemBytes = 404 * 16 + MEL2_FPB * 400 * 16 + MEL2_FPB * 404 * 4 + MEL_BANDS * MEL2_FPB * 4;
+
+__device__ __forceinline__ double2 shfl_d2(double2 v, int src_lane) {
+    return make_double2(__shfl_sync(0xffffffffu, v.x, src_lane, 16), __shfl_sync(0xffffffffu, v.y, src_lane, 16));
+}
+
+__global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams p) {
+    extern __shared__ uint8_t mel_smem[];
+    double2* tw = reinterpret_cast<double2*>(mel_smem);                 // [401] exp(-2 pi i m / 800)  (+3 pad)
+    double2* ybuf = tw + 404;                                            // [FPB][16][25]
+    float* mags = reinterpret_cast<float*>(ybuf + MEL2_FPB * 400);       // [FPB][404]
+    float* outs = mags + MEL2_FPB * 404;                                 // [80][FPB]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 401; i += MEL2_THREADS) tw[i] = p.tw[i];
+    __syncthreads();
+
+    // ---------------- step 1: thread = (frame f, n1) ----------------
+    if (tid < MEL2_FPB * 25) {
+        const int f = tid / 25, n1 = tid % 25;
+        const long long t = (long long)blockIdx.x * MEL2_FPB + f;
+        if (t < p.F) {
+            const double2 ca = tw[2 * n1];       // (cos a, -sin a), a = 2 pi (2 n1) / 800   — also W400^n1
+            const double2 cb = tw[2 * n1 + 1];   // the odd sample of the pair
+            double2 v[16];
+            const long long base = t * MEL_HOP - MEL_NFFT / 2 + 2 * n1;
+#pragma unroll
+            for (int n2 = 0; n2 < 16; ++n2) {
+                const long long j0 = base + 50 * n2;
+                double y0, y1;
+                if (j0 >= 1 && j0 + 1 < p.L) {   // interior: three consecutive samples
+                    const double xm = (double)__ldg(p.wav + j0 - 1), x0 = (double)__ldg(p.wav + j0), x1 = (double)__ldg(p.wav + j0 + 1);
+                    y0 = x0 + (-0.97) * xm;
+                    y1 = x1 + (-0.97) * x0;
+                } else {                         // np.pad(mode="reflect") of the PRE-EMPHASISED signal
+                    double yy[2];
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        long long j = j0 + e;
+                        while (j < 0 || j >= p.L) j = j < 0 ? -j : 2 * (p.L - 1) - j;
+                        const double x0 = (double)__ldg(p.wav + j);
+                        yy[e] = (j > 0) ? x0 + (-0.97) * (double)__ldg(p.wav + j - 1) : x0;
+                    }
+                    y0 = yy[0]; y1 = yy[1];
+                }
+                // periodic Hann: 0.5 - 0.5 cos(a + n2 pi/8),  cos(a + phi) = cos a cos phi - sin a sin phi,  sin a = -ca.y
+                const double c0 = ca.x * kMelC8[n2].x + ca.y * kMelC8[n2].y;
+                const double c1 = cb.x * kMelC8[n2].x + cb.y * kMelC8[n2].y;
+                v[n2] = make_double2((0.5 - 0.5 * c0) * y0, (0.5 - 0.5 * c1) * y1);
+            }
+            // 16-point FFT over n2 = 4 a + b  ->  k2 = c + 4 d
+            double2 u[4][4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                double2 q[4] = {v[b], v[4 + b], v[8 + b], v[12 + b]};
+                butterfly<4>(q);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) u[b][c] = (b * c == 0) ? q[c] : cmul(q[c], kMelW16[b * c]);
+            }
+            double2 pw = make_double2(1.0, 0.0);
+            double2 Y[16];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                double2 q[4] = {u[0][c], u[1][c], u[2][c], u[3][c]};
+                butterfly<4>(q);
+#pragma unroll
+                for (int d = 0; d < 4; ++d) Y[c + 4 * d] = q[d];
+            }
+            double2* dst = ybuf + f * 400 + n1;
+            dst[0] = Y[0];
+#pragma unroll
+            for (int k2 = 1; k2 < 16; ++k2) {      // W400^(n1 k2) by recurrence from W400^n1
+                pw = cmul(pw, ca);
+                dst[k2 * 25] = cmul(Y[k2], pw);
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---------------- step 3: thread = (frame f, k2), whole warps so that the shuffles below are convergent ----------------
+    if (tid < 96) {
+        const int f = tid >> 4, k2 = tid & 15;
+        const long long t = (long long)blockIdx.x * MEL2_FPB + f;
+        const bool live = f < MEL2_FPB && t < p.F;
+        double2 y[25];
+#pragma unroll
+        for (int n1 = 0; n1 < 25; ++n1) y[n1] = live ? ybuf[f * 400 + k2 * 25 + n1] : make_double2(0.0, 0.0);
+        // 25-point FFT over n1 = 5 a + b  ->  k1 = c + 5 d
+        double2 u[5][5];
+#pragma unroll
+        for (int b = 0; b < 5; ++b) {
+            double2 q[5] = {y[b], y[5 + b], y[10 + b], y[15 + b], y[20 + b]};
+            butterfly<5>(q);
+#pragma unroll
+            for (int c = 0; c < 5; ++c) u[b][c] = (b * c == 0) ? q[c] : cmul(q[c], kMelW25[b * c]);
+        }
+        double2 Z[25];
+#pragma unroll
+        for (int c = 0; c < 5; ++c) {
+            double2 q[5] = {u[0][c], u[1][c], u[2][c], u[3][c], u[4][c]};
+            butterfly<5>(q);
+#pragma unroll
+            for (int d = 0; d < 5; ++d) Z[c + 5 * d] = q[d];
+        }
+        // real-FFT split: bin k = k2 + 16 k1 pairs with 400 - k = (16 - k2) + 16 (24 - k1): lane (16 - k2) & 15, register 24 - k1
+        const int partner = (16 - k2) & 15;
+        const double2 wk2 = live ? tw[k2] : make_double2(1.0, 0.0);
+        float* mag = mags + f * 404;
+#pragma unroll
+        for (int k1 = 0; k1 < 25; ++k1) {
+            double2 zp = shfl_d2(Z[24 - k1], partner);
+            if (k2 == 0) zp = (k1 == 0) ? Z[0] : Z[25 - k1];    // 400 - 16 k1 = 16 (25 - k1): same lane
+            const double2 zk = Z[k1];
+            const double2 e = make_double2(0.5 * (zk.x + zp.x), 0.5 * (zk.y - zp.y));
+            const double2 dd = make_double2(0.5 * (zk.x - zp.x), 0.5 * (zk.y + zp.y));
+            const double2 o = make_double2(dd.y, -dd.x);         // -i d
+            const double2 x = cadd(e, cmul(cmul(wk2, kMelW50[k1]), o));
+            const float re = (float)x.x, im = (float)x.y;        // complex64 store of librosa.stft
+            if (live) mag[k2 + 16 * k1] = (float)sqrt((double)re * (double)re + (double)im * (double)im);
+        }
+        if (live && k2 == 0) {                                   // Nyquist bin: X[400] = E[0] - O[0] = Re Z[0] - Im Z[0]
+            const float re = (float)(Z[0].x - Z[0].y);
+            mag[400] = fabsf(re);
+        }
+    }
+    __syncthreads();
+    // ---------------- sparse mel product + dB + normalise / clip, fp32 as NumPy does on float32 arrays ----------------
+    for (int i = tid; i < MEL_BANDS * MEL2_FPB; i += MEL2_THREADS) {
+        const int f = i / MEL_BANDS, m = i % MEL_BANDS;
+        const long long t = (long long)blockIdx.x * MEL2_FPB + f;
+        if (t >= p.F) continue;
+        const float* mag = mags + f * 404;
+        const int off = p.boff[m], st = p.bstart[m], len = p.blen[m];
+        float s = 0.0f;
+        for (int j = 0; j < len; ++j) s = fmaf(__ldg(p.bvals + off + j), mag[st + j], s);
+        const float db = 20.0f * log10f(fmaxf(1e-5f, s)) - 20.0f;
+        float v = 8.0f * ((db + 100.0f) / 100.0f) - 4.0f;
+        v = fminf(fmaxf(v, -4.0f), 4.0f);
+        outs[m * MEL2_FPB + f] = v;
+    }
+    __syncthreads();
+    for (int i = tid; i < MEL_BANDS * MEL2_FPB; i += MEL2_THREADS) {
+        const int m = i / MEL2_FPB, ff = i % MEL2_FPB;
+        const long long tt = (long long)blockIdx.x * MEL2_FPB + ff;
+        if (tt < p.F) p.mel[(long long)m * p.F + tt] = outs[i];
+    }
+}
 
 }  // namespace w2l

@@ -116,6 +116,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_rowstack = enabled("W2L_DISABLE_ROWSTACK");
         ctx->use_side = enabled("W2L_DISABLE_SIDESTREAM");
         ctx->use_pdl = enabled("W2L_DISABLE_PDL");
+        ctx->use_mel_v2 = enabled("W2L_DISABLE_MELV2");
         if (ctx->x2) {  // the split-operand mode runs on the generic kernel with the direct epilogue only
             ctx->use_patch = ctx->use_fold = ctx->use_fold_s2 = ctx->use_ctfused = ctx->use_tma_epi = false;
         }
@@ -566,8 +567,13 @@ int w2l_melspectrogram(w2l_ctx* ctx, const float* wav, int64_t n_samples, float*
     MelParams p;
     p.wav = wav; p.L = n_samples; p.mel = mel; p.F = w2l_mel_num_frames(n_samples);
     p.tw = ctx->mel_tw; p.bvals = ctx->mel_bvals; p.boff = ctx->mel_boff; p.bstart = ctx->mel_bstart; p.blen = ctx->mel_blen;
-    const long long blocks = (p.F + MEL_FPB - 1) / MEL_FPB;
-    mel_kernel<<<(unsigned)blocks, MEL_FPB * MEL_TPF, kMelSmemBytes, (cudaStream_t)stream>>>(p);
+    if (ctx->use_mel_v2) {   // FFT in registers (mel.cuh, round 2); W2L_DISABLE_MELV2=1 selects the shared-memory version
+        const long long blocks = (p.F + MEL2_FPB - 1) / MEL2_FPB;
+        mel_kernel_v2<<<(unsigned)blocks, MEL2_THREADS, kMel2SmemBytes, (cudaStream_t)stream>>>(p);
+    } else {
+        const long long blocks = (p.F + MEL_FPB - 1) / MEL_FPB;
+        mel_kernel<<<(unsigned)blocks, MEL_FPB * MEL_TPF, kMelSmemBytes, (cudaStream_t)stream>>>(p);
+    }
     ctx->launches++;
     CK(cudaGetLastError());
     return W2L_OK;
