@@ -344,6 +344,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the SyncNet / disc / mel side measurements")
     ap.add_argument("--profile-out", default=None, help="write the per-launch table to this file")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, the driver's mode): --batch windows PER GPU.  strong: --batch is the GLOBAL batch, split over the ranks")
     ap.add_argument("--workload", default="infer", choices=["infer", "train"],
                     help="infer: the headline metric (default).  train: BASELINE configs[4], one training iteration per step")
     args = ap.parse_args()
@@ -389,6 +391,10 @@ def main():
             dist.destroy_process_group()
         return
     B, T = args.batch, args.frames
+    if args.scaling == "strong":
+        if args.batch % world != 0:
+            raise SystemExit("--scaling strong needs --batch divisible by the number of GPUs")
+        B = args.batch // world      # whole T-windows per rank (parallel.shard_range): the t-major flatten stays local
     N = B * T
 
     # weights + inputs (seeded; every rank its own input seed, identical weights)
@@ -439,6 +445,11 @@ def main():
         barrier()
         launches = ctx.launch_count() - l0
         ms = e0.elapsed_time(e1)
+        per_rank_ms = [ms / args.steps]
+        if world > 1:   # every rank's own device time: the spread shows whether a slow step is clocks or code
+            box = [None] * world
+            dist.all_gather_object(box, ms / args.steps)
+            per_rank_ms = [float(v) for v in box]
         ms = max_over_ranks(ms, dev)
         clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
         ms_per_step = ms / args.steps
@@ -545,8 +556,8 @@ def main():
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f16", "data": "synthetic",
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f16", "data": "synthetic", "per_rank_ms_per_step": per_rank_ms,
             "config": {"workload": f"BASELINE configs[1] at the metric's B={B}, T={T}: Wav2Lip.forward eval, {N} crops/GPU/step, fp32 NCHW in/out",
                        "per_gpu_batch": N, "global_batch": N * world, "parallelism": f"replicas x{world}, batch-sharded, no collective",
                        "weights": "seeded random (reference default-init statistics + randomised BatchNorm)",

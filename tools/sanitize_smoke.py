@@ -21,5 +21,22 @@ with torch.no_grad():
     p = d(torch.rand(2, 3, 2, 96, 96).cuda())
     m = audio.melspectrogram(np.random.randn(5000).astype(np.float32))
     c = audio.mel_chunks(m, 25.0)
+    ms = audio.melspectrogram(np.random.randn(57).astype(np.float32))           # multi-fold reflect padding
+    # scope row f2: crop + resize, paste, the whole inner loop in one call
+    frames = torch.randint(0, 256, (2, 72, 88, 3), dtype=torch.uint8).cuda()
+    boxes = [[0, 5, 60, 7, 80], [1, 0, 72, 0, 88]]
+    cr = g.crop_resize(frames, boxes)
+    pa = g.paste(u[:2], frames, boxes)
+    fr = g.infer_frames(torch.rand(2, 1, 80, 16).cuda(), frames, boxes)
     torch.cuda.synchronize()
+# scope row f1: one training iteration through the autograd bridge and one fused native step (B=1, T=5)
+from wav2lip_b200.training import Wav2LipTrainStep
+gt_ = Wav2Lip().cuda().train()
+out = gt_(torch.rand(2, 1, 80, 16).cuda(), torch.rand(2, 6, 96, 96).cuda())
+out.mean().backward()
+ex = SyncNet_color().cuda().train()
+step = Wav2LipTrainStep(Wav2Lip().cuda().train(), ex, lr=1e-4, syncnet_wt=0.03)
+ls = step(torch.rand(1, 6, 5, 96, 96).cuda(), torch.rand(1, 5, 1, 80, 16).cuda(), torch.rand(1, 1, 80, 16).cuda(), torch.rand(1, 3, 5, 96, 96).cuda())
+torch.cuda.synchronize()
+print("train ok", [float(v) for v in ls.cpu()])
 print("ok", y.shape, y5.shape, u.shape, a.shape, p.shape, m.shape, c.shape, float(y.mean()), float(p.mean()))
