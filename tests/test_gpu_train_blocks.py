@@ -4,10 +4,14 @@ dbias, running-average update) — through the C-ABI entry `w2l_conv_block_train
 the three networks, against oracle/backward_recipe.py (float64; itself equal to torch autograd, tests/
 test_backward_recipe.py).
 
-Tolerances: operands (activations, weights, incoming gradients) are rounded to bf16 (8-bit mantissa, 2^-9 relative)
-and every stored intermediate (z, y, dz) once more; accumulation, statistics and reductions are fp32/fp64.  Per block
-that is a few 1e-3 relative in the L2 sense (tests/test_precision_model.py: "a single block's backward in bf16 is within
-3 %"); asserted: relative L2 error <= 2e-2 for y / dx / dW, <= 2e-2 for dgamma / dbeta."""
+Two bars per case:
+  * SAME ROUNDING POINTS (the parity bar): the reference below is the float64 recipe with the
+    kernels' own rounding points — bf16 operands (x, w, dy), z stored in bf16 before the statistics, y / dz / du stored in
+    bf16 — so what remains is fp32-vs-fp64 accumulation and the rare 1-ulp bf16 rounding flip: relative L2 <= 5e-3 on
+    y, dx, dW, dgamma, dbeta, dbias.
+  * EXACT OPERANDS (information, loose): against the unrounded float64 recipe the same tensors differ by 3-9 % — the
+    ReLU / LeakyReLU mask of the ~0.2 % of pre-activations that sit within bf16 rounding of zero flips, and a flipped
+    element carries a full-size error (tests/test_precision_model.py measures the same 3 % on the CPU); asserted <= 0.15."""
 import ctypes as C
 
 import pytest
@@ -18,7 +22,50 @@ from oracle import w2l_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-REL = 2e-2
+REL = 5e-3       # same rounding points
+LOOSE = 0.15     # exact operands
+
+
+def bf16(t):
+    return t.to(torch.bfloat16).to(torch.float64)
+
+
+def reference_same_rounding(x, w, b, gamma, beta, dy, row):
+    """float64 block forward / backward with the kernels' rounding points (see the module docstring)."""
+    kind, _cin, _cout, k, s, p, op, res = row
+    F = torch.nn.functional
+    xq, wq, dyq = bf16(x), bf16(w), bf16(dy)
+    if kind == "t":
+        z = F.conv_transpose2d(xq, wq, None, stride=O._pair(s), padding=O._pair(p), output_padding=O._pair(op))
+    else:
+        z = F.conv2d(xq, wq, None, stride=O._pair(s), padding=O._pair(p))
+    if kind == "n":
+        y = bf16(F.leaky_relu(z + b.double()[None, :, None, None], 0.01))
+        dz = bf16(dyq * torch.where(y > 0, torch.ones_like(y), torch.full_like(y, 0.01)))
+        out = {"y": y, "db": dz.sum(dim=(0, 2, 3)), "dgamma": None, "dbeta": None}
+        du = None
+    else:
+        zr = bf16(z)                                        # the conv epilogue stores z in bf16; the bias never enters
+        mean = zr.mean(dim=(0, 2, 3))
+        var = zr.var(dim=(0, 2, 3), unbiased=False)
+        invstd = (var + 1e-5).rsqrt()
+        zhat = (zr - mean[None, :, None, None]) * invstd[None, :, None, None]
+        u = zhat * gamma.double()[None, :, None, None] + beta.double()[None, :, None, None]
+        if res:
+            u = u + xq
+        y = bf16(F.relu(u))
+        du = dyq * (y > 0).to(torch.float64)
+        m = du.numel() / du.shape[1]
+        dbeta = du.sum(dim=(0, 2, 3))
+        dgamma = (du * zhat).sum(dim=(0, 2, 3))
+        dz = bf16((gamma.double() * invstd)[None, :, None, None] * (du - dbeta[None, :, None, None] / m - zhat * dgamma[None, :, None, None] / m))
+        out = {"y": y, "dgamma": dgamma, "dbeta": dbeta, "db": None, "zmean": mean, "zvar": var}
+    dx = R.conv_dgrad(dz, wq, row, (x.shape[2], x.shape[3]))
+    if kind != "n" and res:
+        dx = dx + bf16(du)
+    out["dx"] = dx
+    out["dw"] = R.conv_wgrad(xq, dz, row)
+    return out
 
 
 def rel_l2(got, ref):
@@ -87,7 +134,8 @@ def test_block_train_forward_backward(case, ctx):
     rmean, rvar = 0.1 * torch.randn(cout, generator=g), 0.5 + torch.rand(cout, generator=g)
     y_ref, saved = R.block_forward_train(x.double(), w.double(), b.double(), gamma.double(), beta.double(), row)
     dy = torch.randn(y_ref.shape, generator=g)
-    ref = R.block_backward(dy.double(), x.double(), w.double(), gamma.double(), row, saved)
+    ref = R.block_backward(dy.double(), x.double(), w.double(), gamma.double(), row, saved)     # exact operands
+    same = reference_same_rounding(x, w, b, gamma, beta, dy, row)                                   # the kernels' rounding points
 
     li = _lib.LayerInfo()
     li.name = b"block"
@@ -106,21 +154,21 @@ def test_block_train_forward_backward(case, ctx):
                                             P(bed) if bn else None, P(rmd) if bn else None, P(rvd) if bn else None, P(dyd), P(yd),
                                             P(dxd), P(dwd), P(dbd), P(dgd) if bn else None, P(dbed) if bn else None, None))
     torch.cuda.synchronize()
-    assert rel_l2(yd.cpu(), y_ref) <= REL, ("y", rel_l2(yd.cpu(), y_ref))
-    assert rel_l2(dxd.cpu(), ref["dx"]) <= REL, ("dx", rel_l2(dxd.cpu(), ref["dx"]))
-    assert rel_l2(dwd.cpu(), ref["dw"]) <= REL, ("dw", rel_l2(dwd.cpu(), ref["dw"]))
+    errs = {"y": rel_l2(yd.cpu(), same["y"]), "dx": rel_l2(dxd.cpu(), same["dx"]), "dw": rel_l2(dwd.cpu(), same["dw"])}
+    loose = {"y": rel_l2(yd.cpu(), y_ref), "dx": rel_l2(dxd.cpu(), ref["dx"]), "dw": rel_l2(dwd.cpu(), ref["dw"])}
     if bn:
-        assert rel_l2(dgd.cpu(), ref["dgamma"]) <= REL, ("dgamma", rel_l2(dgd.cpu(), ref["dgamma"]))
-        assert rel_l2(dbed.cpu(), ref["dbeta"]) <= REL, ("dbeta", rel_l2(dbed.cpu(), ref["dbeta"]))
-        assert dbd.abs().max().item() == 0.0          # conv bias under a BatchNorm: exactly zero gradient
+        errs["dgamma"] = rel_l2(dgd.cpu(), same["dgamma"])
+        errs["dbeta"] = rel_l2(dbed.cpu(), same["dbeta"])
+        errs["dbias_abs"] = dbd.abs().max().item()    # conv bias under a BatchNorm: exactly zero gradient
         # running averages as nn.BatchNorm2d updates them (momentum 0.1, unbiased variance, conv bias included in the mean)
-        if kind == "t":
-            z = torch.nn.functional.conv_transpose2d(x.double(), w.double(), b.double(), stride=(sh, sw), padding=(ph, pw), output_padding=op)
-        else:
-            z = torch.nn.functional.conv2d(x.double(), w.double(), b.double(), stride=(sh, sw), padding=(ph, pw))
-        m_ref = 0.9 * rmean.double() + 0.1 * z.mean(dim=(0, 2, 3))
-        v_ref = 0.9 * rvar.double() + 0.1 * z.var(dim=(0, 2, 3), unbiased=True)
-        assert (rmd.cpu().double() - m_ref).abs().max().item() <= 5e-3
-        assert rel_l2(rvd.cpu(), v_ref) <= 1e-2
+        m = same["y"].numel() / cout
+        m_ref = 0.9 * rmean.double() + 0.1 * (same["zmean"] + b.double())
+        v_ref = 0.9 * rvar.double() + 0.1 * same["zvar"] * m / (m - 1)
+        errs["rmean"] = rel_l2(rmd.cpu(), m_ref)
+        errs["rvar"] = rel_l2(rvd.cpu(), v_ref)
     else:
-        assert rel_l2(dbd.cpu(), ref["db"]) <= REL, ("db", rel_l2(dbd.cpu(), ref["db"]))
+        errs["db"] = rel_l2(dbd.cpu(), same["db"])
+        loose["db"] = rel_l2(dbd.cpu(), ref["db"])
+    bad = {k: v for k, v in errs.items() if not (v <= REL)}
+    bad.update({"loose_" + k: v for k, v in loose.items() if not (v <= LOOSE)})
+    assert not bad, ({k: float(f"{v:.3g}") for k, v in errs.items()}, {k: float(f"{v:.3g}") for k, v in loose.items()})

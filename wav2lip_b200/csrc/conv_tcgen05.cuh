@@ -230,8 +230,10 @@ struct ConvCfg {
 // cleared through w2l_f16_overflow().  bf16 has fp32's exponent range and never sets it.
 __device__ int g_f16_overflow = 0;
 
+// `live` = the value belongs to a real output pixel.  (GEMM rows beyond a partial tile box are computed from stale shared
+// memory — any bit pattern, NaN included — and never stored; they must not raise the flag.)
 template <bool kBF16>
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
+__device__ __forceinline__ uint32_t pack2(float a, float b, bool live = true) {
     if constexpr (kBF16) {
         __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&h);
@@ -239,7 +241,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
         __half2 h = __floats2half2_rn(a, b);
         const uint32_t u = *reinterpret_cast<uint32_t*>(&h);
         // exponent field all ones (inf / NaN) in either half: adding 0x0400 to the magnitude bits carries into bit 15
-        if (((u & 0x7FFF7FFFu) + 0x04000400u) & 0x80008000u) g_f16_overflow = 1;
+        if (live && (((u & 0x7FFF7FFFu) + 0x04000400u) & 0x80008000u)) g_f16_overflow = 1;
         return u;
     }
 }
@@ -567,8 +569,9 @@ __global__ void __launch_bounds__(ConvCfg<BN, BK, MT>::kThreads, 1) conv_igemm_k
 #pragma unroll
                             for (int i = 0; i < 8; ++i) f[i] = f[i] > 0.0f ? f[i] : 0.01f * f[i];
                         }
-                        const uint32_t o0 = pack2<kBF16>(f[0], f[1]), o1 = pack2<kBF16>(f[2], f[3]);
-                        const uint32_t o2 = pack2<kBF16>(f[4], f[5]), o3 = pack2<kBF16>(f[6], f[7]);
+                        const bool live = row < rows_valid;
+                        const uint32_t o0 = pack2<kBF16>(f[0], f[1], live), o1 = pack2<kBF16>(f[2], f[3], live);
+                        const uint32_t o2 = pack2<kBF16>(f[4], f[5], live), o3 = pack2<kBF16>(f[6], f[7], live);
                         asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
                     }
                     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

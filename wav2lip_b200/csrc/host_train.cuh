@@ -48,7 +48,9 @@ struct TrainPlan {
     Plan pl;                       // op storage + allocations
     NetW wf, wd;                   // forward / dgrad weight slabs (16-bit), repacked every step
     std::vector<PackParams> pack_jobs;
+    std::vector<PackFoldParams> pack_fold_jobs;
     std::vector<FoldJob> fold_jobs;
+    bool allow_fold = false, allow_rowstack = false;   // the context's own switches (the builder turns them off around itself)
     std::vector<TBlock> blocks;    // forward order
     std::vector<size_t> ingest;    // indices of the ingest ops
     // generator
@@ -279,8 +281,8 @@ static int launch_wgrad(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool accumulate,
     CK(launch_k(e->fn, b.wg.grid, kWgThreads, (size_t)b.wg.smem, st, b.wg.wp, ctx->use_pdl));
     WgradReduceParams rp = b.wg.rp;
     rp.ws = tp->wg_ws; rp.out = b.gW; rp.accumulate = accumulate ? 1 : 0;
-    const long long total = (long long)rp.Cm * rp.Cn;
-    wgrad_reduce_kernel<<<(int)std::min<long long>((total + 127) / 128, ctx->num_sms * 8), 128, 0, st>>>(rp);
+    const int n_tiles64 = (rp.Cn + 63) / 64;
+    wgrad_reduce_kernel<<<dim3((unsigned)n_tiles64, (unsigned)rp.Cm), 256, (size_t)64 * (rp.ntaps + 1) * 4, st>>>(rp);
     ctx->launches += 2;
     return W2L_OK;
 }
@@ -288,11 +290,17 @@ static int launch_wgrad(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool accumulate,
 // dense 16-bit activation owned by the plan
 static int tp_act(TrainPlan* tp, Act* a, int N, int H, int W, int C) { return plan_act(&tp->pl, a, N, H, W, C); }
 
+// First blocks (fed by a caller tensor): the forward conv may read a second, K-folded copy of the input (the inference
+// plan's first-layer layout, 10-20x faster on the 7x7 / 6-channel layer) written by one more ingest launch; the backward
+// (wgrad) reads the plain NHWC copy.
+struct FoldIn { bool on = false; int src_id = 0, B = 0, C = 0; long long sB = 0, sC = 0, sT = 0; int y_off = 0, Wsrc = 0, cgrp = 0; long long sG = 0; };
+
 // Add one block to a training plan: forward launches, statistics buffers, dgrad launches, wgrad.
 //   x / y: input and output views;   dy: gradient view of y;   dx: where the input gradient goes (base nullptr: none);
 //   dx_add: extra gradient added to dx (skip half of a concat gradient), base nullptr: none.
 static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const Layer& L, const Act& x, const Act& y, const Act& dy,
-                           const Act& dx, const Act& dx_add, bool want_wgrad, bool in_hw1, size_t* ws_need, float* y_f32 = nullptr) {
+                           const Act& dx, const Act& dx_add, bool want_wgrad, bool in_hw1, size_t* ws_need, float* y_f32 = nullptr,
+                           const FoldIn* fold = nullptr) {
     TrainState* ts = train_state(ctx);
     TBlock b;
     b.li = li; b.L = L; b.x = x; b.y = y; b.dy = dy; b.dx = dx; b.dx_add = dx_add; b.y_f32 = y_f32;
@@ -311,18 +319,33 @@ static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const L
     cudaStream_t st = nullptr;
     // ---- forward weights + launches ----
     if ((int)tp->wf.layers.size() <= li) { tp->wf.layers.resize(li + 1); tp->wd.layers.resize(li + 1); }
-    ctx->pack_rec = &tp->pack_jobs; ctx->fold_rec = &tp->fold_jobs;
-    int r = load_layer(ctx, &tp->wf.layers[li], L, b.W, b.bn ? nullptr : b.b, nullptr, nullptr, nullptr, nullptr, in_hw1, false, st);
+    ctx->pack_rec = &tp->pack_jobs; ctx->fold_rec = &tp->fold_jobs; ctx->pack_fold_rec = &tp->pack_fold_jobs;
+    const bool use_fold_fwd = fold && fold->on && tp->allow_fold && !dx.base;
+    if (use_fold_fwd) { ctx->use_fold = true; ctx->use_rowstack = tp->allow_rowstack; }
+    int r = load_layer(ctx, &tp->wf.layers[li], L, b.W, b.bn ? nullptr : b.b, nullptr, nullptr, nullptr, nullptr, in_hw1, use_fold_fwd, st);
+    ctx->pack_fold_rec = nullptr;
     if (r == W2L_OK && dx.base) {
         b.Ld = dgrad_layer(L, x.H, x.W, y.H, y.W);
         r = load_dgrad_layer(ctx, &tp->wd.layers[li], L, b.Ld, b.W, st);
     }
     ctx->pack_rec = nullptr; ctx->fold_rec = nullptr;
-    CKR(r);
+    if (r != W2L_OK) { if (use_fold_fwd) { ctx->use_fold = false; ctx->use_rowstack = false; } return r; }
     Act conv_out = y;
     if (b.bn) { CKR(tp_act(tp, &b.z, y.N, y.H, y.W, L.cout)); conv_out = b.z; }
+    Act x_fwd = x;
+    if (use_fold_fwd && tp->wf.layers[li].ph[0].fold) {
+        int rr = plan_input_act(&tp->pl, &x_fwd, x.N, x.H, x.W, L.cin, tp->wf.layers[li], L);
+        if (rr != W2L_OK) { ctx->use_fold = false; ctx->use_rowstack = false; return rr; }
+        add_ingest(&tp->pl, "ingest.fold", fold->src_id, x_fwd, fold->B, fold->C, fold->sB, fold->sC, fold->sT, fold->y_off, fold->Wsrc);
+        tp->pl.ops.back().ip.cgrp = fold->cgrp; tp->pl.ops.back().ip.sG = fold->sG;
+        tp->ingest.push_back(tp->pl.ops.size() - 1);
+    }
     b.fwd0 = tp->pl.ops.size();
-    CKR(emit_block(ctx, &tp->pl, tp->wf, li, L, x, conv_out, nullptr, false, 1, 1, b.bn ? ACT_NONE : -1));
+    {
+        const int rr = emit_block(ctx, &tp->pl, tp->wf, li, L, x_fwd, conv_out, nullptr, false, 1, 1, b.bn ? ACT_NONE : -1);
+        if (use_fold_fwd) { ctx->use_fold = false; ctx->use_rowstack = false; }
+        CKR(rr);
+    }
     b.fwd1 = tp->pl.ops.size();
     for (size_t i = b.fwd0; i < b.fwd1; ++i) tp->fwd_flops += tp->pl.ops[i].flops;
     // ---- statistics / reduction buffers ----
@@ -359,7 +382,7 @@ static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const L
 //   its gradient view (base nullptr: allocate dense ones, returned through out / dout)
 static int add_train_chain(w2l_ctx* ctx, TrainPlan* tp, int net, const std::vector<Layer>& layers, const std::vector<int>& idx,
                            Act x0, Act dx0, Act dx0_add, const Act* last, const Act* dlast, bool want_wgrad, size_t* ws_need,
-                           Act* out, Act* dout, float* last_f32 = nullptr) {
+                           Act* out, Act* dout, float* last_f32 = nullptr, const FoldIn* fold = nullptr) {
     // values and gradients of every block output first (the gradient view of y[k] is the dx of block k+1)
     std::vector<Act> ys(idx.size()), dys(idx.size());
     int H = x0.H, W = x0.W;
@@ -383,7 +406,7 @@ static int add_train_chain(w2l_ctx* ctx, TrainPlan* tp, int net, const std::vect
         const Act& dx = k == 0 ? dx0 : dys[k - 1];
         const bool hw1 = L.kind == W2L_BLOCK_CONVT_BN_RELU && x.H == 1 && x.W == 1;
         CKR(add_train_block(ctx, tp, net, idx[k], L, x, ys[k], dys[k], dx, k == 0 ? dx0_add : none, want_wgrad, hw1, ws_need,
-                            k + 1 == idx.size() ? last_f32 : nullptr));
+                            k + 1 == idx.size() ? last_f32 : nullptr, k == 0 ? fold : nullptr));
     }
     if (out) *out = ys.back();
     if (dout) *dout = dys.back();
@@ -406,12 +429,18 @@ static int build_generator_train_plan(w2l_ctx* ctx, TrainPlan* tp, size_t* ws_ne
     Act faceIn, melIn, none;
     CKR(tp_act(tp, &faceIn, N, 96, 96, 16));
     CKR(tp_act(tp, &melIn, N, 80, 16, 16));
+    FoldIn fmel, fface;
+    fmel.on = fface.on = true;
     if (T > 0) {
         add_train_ingest(tp, "ingest.mel", 0, melIn, B, 1, (long long)T * 1280, 1280, 1280, 0, 16);
         add_train_ingest(tp, "ingest.face", 1, faceIn, B, 6, (long long)6 * T * 9216, (long long)T * 9216, 9216, 0, 96);
+        fmel.src_id = 0; fmel.B = B; fmel.C = 1; fmel.sB = (long long)T * 1280; fmel.sC = 1280; fmel.sT = 1280; fmel.Wsrc = 16;
+        fface.src_id = 1; fface.B = B; fface.C = 6; fface.sB = (long long)6 * T * 9216; fface.sC = (long long)T * 9216; fface.sT = 9216; fface.Wsrc = 96;
     } else {
         add_train_ingest(tp, "ingest.mel", 0, melIn, N, 1, 1280, 1280, 0, 0, 16);
         add_train_ingest(tp, "ingest.face", 1, faceIn, N, 6, 6 * 9216, 9216, 0, 0, 96);
+        fmel.src_id = 0; fmel.B = N; fmel.C = 1; fmel.sB = 1280; fmel.sC = 1280; fmel.Wsrc = 16;
+        fface.src_id = 1; fface.B = N; fface.C = 6; fface.sB = 6 * 9216; fface.sC = 9216; fface.Wsrc = 96;
     }
     const int hw[7] = {1, 3, 6, 12, 24, 48, 96};
     const int dec_c[7] = {512, 512, 512, 384, 256, 128, 64};
@@ -423,7 +452,7 @@ static int build_generator_train_plan(w2l_ctx* ctx, TrainPlan* tp, size_t* ws_ne
     }
     // audio encoder
     Act AE, dAE;
-    CKR(add_train_chain(ctx, tp, net, g.layers, g.audio_enc, melIn, none, none, nullptr, nullptr, true, ws_need, &AE, &dAE));
+    CKR(add_train_chain(ctx, tp, net, g.layers, g.audio_enc, melIn, none, none, nullptr, nullptr, true, ws_need, &AE, &dAE, nullptr, &fmel));
     // face encoder: stage i ends in the skip half of D[6-i]; the gradient of a stage output is
     //   (input gradient of the next stage's first block) + (skip half of dD[6-i])  — the latter joins in that dgrad's epilogue
     Act x = faceIn, dx = none;
@@ -433,7 +462,8 @@ static int build_generator_train_plan(w2l_ctx* ctx, TrainPlan* tp, size_t* ws_ne
     for (int i = 0; i < 7; ++i) {
         Act dst = D[6 - i].slice(dec_c[6 - i], skip_c[6 - i]);
         Act add = i > 0 ? dD[6 - (i - 1)].slice(dec_c[6 - (i - 1)], skip_c[6 - (i - 1)]) : none;
-        CKR(add_train_chain(ctx, tp, net, g.layers, g.face_enc[i], x, dx, add, &dst, &G[i], true, ws_need, nullptr, nullptr));
+        CKR(add_train_chain(ctx, tp, net, g.layers, g.face_enc[i], x, dx, add, &dst, &G[i], true, ws_need, nullptr, nullptr, nullptr,
+                            i == 0 ? &fface : nullptr));
         x = dst; dx = G[i];
     }
     // decoder
@@ -510,6 +540,7 @@ static int get_train_plan(w2l_ctx* ctx, int net, int B, int T, bool want_wgrad, 
     // the specialised first-layer paths (K-folded input layouts) are inference-only: training keeps plain NHWC inputs,
     // which is what the wgrad kernel reads
     const bool s_fold = ctx->use_fold, s_rs = ctx->use_rowstack;
+    tp->allow_fold = s_fold && ctx->use_patch; tp->allow_rowstack = s_rs;
     ctx->use_fold = false; ctx->use_rowstack = false;
     size_t ws_need = 0;
     int r;
@@ -538,6 +569,13 @@ static int repack_weights(w2l_ctx* ctx, TrainPlan* tp, cudaStream_t st) {
         const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
         if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
         else pack_w_kernel<false><<<blocks, 256, 0, st>>>(pp);
+        ctx->launches++;
+    }
+    for (const PackFoldParams& fp : tp->pack_fold_jobs) {
+        const size_t n = (size_t)fp.kh * fp.cout_pad * fp.kfold;
+        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+        if (ctx->bf16) pack_fold_kernel<true><<<blocks, 256, 0, st>>>(fp);
+        else pack_fold_kernel<false><<<blocks, 256, 0, st>>>(fp);
         ctx->launches++;
     }
     for (const FoldJob& f : tp->fold_jobs) {
@@ -586,7 +624,7 @@ static int block_forward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool update_run
     memset(&rp, 0, sizeof(rp));
     rp.z = b.z.ptr(); rp.z_pitch = b.z.Cs; rp.partial = b.partial; rp.M = b.M; rp.C = C;
     launch_chan_reduce<0>(ctx, rp, b.nblk, st);
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(b.partial, b.nblk, C, (double)b.M, b.b, update_running ? b.rmean : nullptr,
+    bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, st>>>(b.partial, b.nblk, C, (double)b.M, b.b, update_running ? b.rmean : nullptr,
                                                        update_running ? b.rvar : nullptr, b.stats);
     ctx->launches++;
     BnApplyParams ap;
@@ -612,7 +650,7 @@ static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bo
         rp.z = b.z.ptr(); rp.z_pitch = b.z.Cs; rp.stats = b.stats;
         launch_chan_reduce<1>(ctx, rp, b.nblk, st);
         const bool pg = wgrad && b.ggamma;
-        bn_bwd_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(b.partial, b.nblk, C, (double)b.M, b.gamma, b.stats, pg ? b.ggamma : nullptr,
+        bn_bwd_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, st>>>(b.partial, b.nblk, C, (double)b.M, b.gamma, b.stats, pg ? b.ggamma : nullptr,
                                                            pg ? b.gbeta : nullptr, accumulate ? 1 : 0, b.coef);
         ctx->launches++;
         BnBwdApplyParams ap;
@@ -629,7 +667,7 @@ static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bo
         rp.dz = b.dz.ptr(); rp.dz_pitch = b.dz.Cs;
         launch_chan_reduce<2>(ctx, rp, b.nblk, st);
         if (wgrad && b.gb) {
-            bias_grad_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(b.partial, b.nblk, C, b.gb, accumulate ? 1 : 0);
+            bias_grad_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, st>>>(b.partial, b.nblk, C, b.gb, accumulate ? 1 : 0);
             ctx->launches++;
         }
     }

@@ -161,6 +161,7 @@ struct TrainState;  // host_train.cuh
 struct w2l_ctx {
     std::vector<PackParams>* pack_rec = nullptr;  // when set, pack_taps records its jobs (training re-packs every step)
     std::vector<FoldJob>* fold_rec = nullptr;
+    std::vector<PackFoldParams>* pack_fold_rec = nullptr;
     TrainState* train = nullptr;
     int device = 0;
     bool bf16 = false;

@@ -91,6 +91,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
         fp.src = W; fp.dst = pw.w; fp.kh = L.kh; fp.kw = L.kw; fp.cout = L.cout; fp.cin = L.cin;
         fp.cout_pad = pw.cout_pad; fp.kfold = pw.kfold; fp.Cp = pw.Cp;
         const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
+        if (ctx->pack_fold_rec) ctx->pack_fold_rec->push_back(fp);
         if (ctx->bf16) pack_fold_kernel<true><<<blocks, 256, 0, st>>>(fp);
         else pack_fold_kernel<false><<<blocks, 256, 0, st>>>(fp);
         ctx->launches++;

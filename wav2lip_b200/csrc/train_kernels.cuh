@@ -111,15 +111,34 @@ __global__ void __launch_bounds__(kBnThreads) chan_reduce_kernel(const ChanReduc
     }
 }
 
+// Sum of the per-block partials of 32 consecutive channels in fp64: block = 32 channels x 32 slices of the block range
+// (a one-thread-per-channel loop over ~600 partials is a 70 us latency chain; this is ~3 us).
+constexpr int kFinThreads = 1024;
+__device__ __forceinline__ void sum_partials_2(const float* partial, int nblk, int C, int c, bool cvalid, double* s_out, double* q_out) {
+    __shared__ double sh[2][32][33];
+    const int cl = threadIdx.x & 31, j = threadIdx.x >> 5;
+    double s = 0.0, q = 0.0;
+    if (cvalid)
+        for (int b = j; b < nblk; b += 32) { s += (double)partial[(long long)b * 2 * C + c]; q += (double)partial[(long long)b * 2 * C + C + c]; }
+    sh[0][j][cl] = s; sh[1][j][cl] = q;
+    __syncthreads();
+    if (j == 0) {
+        s = 0.0; q = 0.0;
+#pragma unroll 8
+        for (int k = 0; k < 32; ++k) { s += sh[0][k][cl]; q += sh[1][k][cl]; }
+    }
+    *s_out = s; *q_out = q;
+}
+
 // Batch statistics from the partial sums; running averages updated as nn.BatchNorm2d does in train mode (momentum 0.1,
 // unbiased variance).  The conv bias never enters the conv kernel in train mode (BatchNorm removes any per-channel
-// constant): it only shifts the batch mean, so it is added here, for running_mean.
-__global__ void bn_finalize_kernel(const float* partial, int nblk, int C, double m, const float* bias, float* rmean, float* rvar,
-                                   float* stats) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) { s += (double)partial[(long long)b * 2 * C + c]; q += (double)partial[(long long)b * 2 * C + C + c]; }
+// constant): it only shifts the batch mean, so it is added here, for running_mean.   grid = ceil(C / 32), block = 1024.
+__global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* partial, int nblk, int C, double m, const float* bias, float* rmean,
+                                                                  float* rvar, float* stats) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, q;
+    sum_partials_2(partial, nblk, C, c, c < C, &s, &q);
+    if ((threadIdx.x >> 5) != 0 || c >= C) return;
     const double mean = s / m;
     double var = q / m - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -172,12 +191,12 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnApplyParam
 
 // BatchNorm backward, second half: per-channel sums -> dgamma, dbeta and the three coefficients of
 //   dz = c1 * (du - c2 - zhat * c3),   c1 = gamma * invstd, c2 = mean(du), c3 = mean(du * zhat).
-__global__ void bn_bwd_finalize_kernel(const float* partial, int nblk, int C, double m, const float* gamma, const float* stats,
-                                       float* dgamma, float* dbeta, int accumulate, float* coef) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0, q = 0.0;
-    for (int b = 0; b < nblk; ++b) { s += (double)partial[(long long)b * 2 * C + c]; q += (double)partial[(long long)b * 2 * C + C + c]; }
+__global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const float* partial, int nblk, int C, double m, const float* gamma,
+                                                                      const float* stats, float* dgamma, float* dbeta, int accumulate, float* coef) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, q;
+    sum_partials_2(partial, nblk, C, c, c < C, &s, &q);
+    if ((threadIdx.x >> 5) != 0 || c >= C) return;
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
     if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
     coef[c] = gamma[c] * stats[C + c];
@@ -219,11 +238,11 @@ __global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const BnBwdApp
 }
 
 // per-channel sums of MODE 2 -> conv bias gradient of a nonorm block
-__global__ void bias_grad_finalize_kernel(const float* partial, int nblk, int C, float* db, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= C) return;
-    double s = 0.0;
-    for (int b = 0; b < nblk; ++b) s += (double)partial[(long long)b * 2 * C + c];
+__global__ void __launch_bounds__(kFinThreads) bias_grad_finalize_kernel(const float* partial, int nblk, int C, float* db, int accumulate) {
+    const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+    double s, q;
+    sum_partials_2(partial, nblk, C, c, c < C, &s, &q);
+    if ((threadIdx.x >> 5) != 0 || c >= C) return;
     db[c] = accumulate ? db[c] + (float)s : (float)s;
 }
 

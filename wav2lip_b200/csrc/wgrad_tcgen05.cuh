@@ -16,8 +16,9 @@
 //   warp 0  : TMA producer.  Per K chunk (a bw x bh x bn box of P pixels of the shared grid): 2 loads of the shared
 //             operand's 128-channel tile and, for each tap of the CTA's tap group, the per-tap operand's BN-channel tile
 //             at the shifted / strided position (TMA element strides = the conv stride, out-of-bounds zero fill).
-//   warp 1  : MMA issuer: per chunk P/16 x (taps in the group) tcgen05.mma (M=128, N=BN, K=16); every tap owns BN
-//             accumulator columns of TMEM, so the shared operand is loaded ONCE per chunk for the whole tap group.
+//   warp 1  : MMA issuer: every tap owns BN accumulator columns of TMEM, so the shared operand is loaded ONCE per chunk for
+//             the whole tap group; the taps' tiles lie back to back with a uniform atom stride, so they form ONE operand
+//             of N = taps * BN columns: per chunk P/16 x ceil(taps * BN / 256) tcgen05.mma (M=128, N<=256, K=16).
 //   warp 2  : TMEM allocator (512 columns).
 //   warps 4+: epilogue: tcgen05.ld -> fp32 partial tile -> workspace ws[split][tap][m][n].
 // Split-K over CTAs (a unit = m tile x n tile x tap group x K split) with a deterministic second pass
@@ -149,19 +150,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         // =============================== MMA issuer ===============================
-        constexpr uint32_t idesc = (1u << 4) | ((kBF16 ? 1u : 0u) << 7) | ((kBF16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) |
-                                   (static_cast<uint32_t>(BN >> 3) << 17) | (static_cast<uint32_t>(kTileM >> 4) << 24);
+        // instruction descriptor without the N field: fp32 accumulate, 16-bit operands, A and B both MN-major, M = 128
+        constexpr uint32_t idesc0 = (1u << 4) | ((kBF16 ? 1u : 0u) << 7) | ((kBF16 ? 1u : 0u) << 10) | (1u << 15) | (1u << 16) |
+                                    (static_cast<uint32_t>(kTileM >> 4) << 24);
+        constexpr int kAtomCh = BN >= 64 ? 64 : BN;         // channels of one MN atom of T
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
         const int ksteps = p.P >> 4;
         const uint32_t a_lbo = p.a_bytes >> 1;              // second 64-channel atom of S
-        const uint32_t t_lbo = p.tap_bytes / kAtomsT;       // next 64-channel atom of T
+        // The T tiles of a tap group lie back to back, each made of kAtomsT atoms of P rows: the atom stride P * kRowB is
+        // uniform ACROSS taps, so the whole group is ONE MN-major operand with N = taps * BN — issued in slices of up to 256
+        // columns (e.g. 16 taps of a 16-channel layer per instruction instead of one).
+        const uint32_t t_lbo = p.tap_bytes / kAtomsT;
         for (int u = blockIdx.x; u < total_units; u += gridDim.x, ++it) {
             int g, nt, mt;
             long long c0, c1;
             decode(u, &g, &nt, &mt, &c0, &c1);
             const int nt_g = min(p.tg, p.ntaps - g * p.tg);
+            const int n_total = nt_g * BN;
             mbar_wait(tempty_bar, (it & 1u) ^ 1u);  // the epilogue has drained the accumulators of the previous unit
             tc_fence_after();
             for (long long c = c0; c < c1; ++c) {
@@ -170,10 +177,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_kernel(const __grid_const
                 if (lane == 0) {
                     const uint32_t base = smem_base + stage * p.stage_bytes;
                     const uint64_t adesc = make_mn_desc(base, a_lbo, 1024, 2);
-                    for (int t = 0; t < nt_g; ++t) {
-                        const uint64_t bdesc = make_mn_desc(base + p.a_bytes + t * p.tap_bytes, t_lbo, 8 * kRowB, kLayoutT);
+                    for (int n0 = 0; n0 < n_total; n0 += 256) {
+                        const int nc = min(256, n_total - n0);
+                        const uint32_t idesc = idesc0 | (static_cast<uint32_t>(nc >> 3) << 17);
+                        const uint64_t bdesc = make_mn_desc(base + p.a_bytes + (n0 / kAtomCh) * t_lbo, t_lbo, 8 * kRowB, kLayoutT);
                         for (int k = 0; k < ksteps; ++k)   // 16 pixels further along K: 16 rows of the operand tiles
-                            tc_mma_f16(tmem_base + t * BN, adesc + (uint64_t)((k * 16 * 128) >> 4),
+                            tc_mma_f16(tmem_base + n0, adesc + (uint64_t)((k * 16 * 128) >> 4),
                                        bdesc + (uint64_t)((k * 16 * kRowB) >> 4), idesc, (c > c0 || k > 0) ? 1u : 0u);
                     }
                     tc_commit(empty_bar(stage));
@@ -234,17 +243,31 @@ struct WgradReduceParams {
     int accumulate;
 };
 
-__global__ void wgrad_reduce_kernel(const WgradReduceParams p) {
-    const long long total = (long long)p.Cm * p.Cn;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const int n = (int)(i % p.Cn);
-        const int m = (int)(i / p.Cn);
-        for (int t = 0; t < p.ntaps; ++t) {
-            float s = 0.0f;
-            for (int k = 0; k < p.splits; ++k) s += __ldg(p.ws + (((long long)k * p.ntaps + t) * p.Mp + m) * p.Np + n);
-            float* o = p.out + i * p.ntaps + t;
-            *o = p.accumulate ? *o + s : s;
+// grid = (ceil(Cn / 64), Cm), block = 256: a block sums the splits of one row m, 64 columns n, all taps — reading the
+// workspace in 256-byte runs along n — and transposes through shared memory so that the (n, tap) values leave as one
+// contiguous run of 64 * ntaps floats of the parameter tensor.
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReduceParams p) {
+    extern __shared__ float red_t[];           // [64][ntaps + 1]
+    const int m = blockIdx.y, n0 = blockIdx.x * 64;
+    const int pitch = p.ntaps + 1;
+    const int items = p.ntaps * 64;
+    for (int i = threadIdx.x; i < items; i += 256) {
+        const int t = i >> 6, n = i & 63;
+        float s = 0.0f;
+        if (n0 + n < p.Cn) {
+            const float* src = p.ws + ((long long)t * p.Mp + m) * p.Np + n0 + n;
+            const long long split_stride = (long long)p.ntaps * p.Mp * p.Np;
+            for (int k = 0; k < p.splits; ++k) s += __ldg(src + k * split_stride);
         }
+        red_t[n * pitch + t] = s;
+    }
+    __syncthreads();
+    const int ncols = min(64, p.Cn - n0);
+    float* out = p.out + ((long long)m * p.Cn + n0) * p.ntaps;
+    for (int i = threadIdx.x; i < ncols * p.ntaps; i += 256) {
+        const int n = i / p.ntaps, t = i - n * p.ntaps;
+        const float v = red_t[n * pitch + t];
+        out[i] = p.accumulate ? out[i] + v : v;
     }
 }
 
