@@ -237,7 +237,7 @@ def measure_extra(dev):
     return out
 
 
-def measure_train(dev, rank, world, steps, warmup, B=64, T=5, syncnet_wt=0.03):
+def measure_train(dev, rank, world, steps, warmup, B=64, T=5, syncnet_wt=0.03, profile_out=None):
     """BASELINE configs[4]: one wav2lip_train.py:210-231 iteration per step (generator train-mode forward, get_sync_loss
     through the frozen expert, L1, backward, gradient all-reduce over NCCL when world > 1, Adam), bf16 operands, B=64
     windows x T=5 frames per GPU, everything native (w2l_wav2lip_train_step).  Inputs resident on the device; CUDA-event
@@ -288,6 +288,14 @@ def measure_train(dev, rank, world, steps, warmup, B=64, T=5, syncnet_wt=0.03):
     flop = 3.0 * gen_f + 2.0 * syn_f       # forward + dgrad + wgrad of the generator; forward + dgrad of the frozen expert
     lv = [float(v) for v in losses.cpu()]
     n_param = sum(p.numel() for p in model.parameters())
+    if profile_out and rank == 0:
+        rows = ctx.train_profile(_lib.NET_GENERATOR, iters=3, stream=stream.cuda_stream) + \
+            [("expert:" + n, m, f) for n, m, f in ctx.train_profile(_lib.NET_SYNCNET, iters=3, stream=stream.cuda_stream)]
+        tot = sum(m for _, m, _ in rows)
+        with open(profile_out, "w") as f:
+            f.write(f"# per-stage CUDA-event times of one training iteration, B={B} T={T}; {len(rows)} stages, sum {tot:.3f} ms (stages timed warm, back to back)\n")
+            for n, m, fl in rows:
+                f.write(f"{n:44s} {m * 1e3:10.1f} us {fl / m / 1e9 if m > 0 and fl > 0 else 0:9.1f} TFLOP/s {100 * m / tot:5.1f}%\n")
     return {"config": f"wav2lip_train.py step (gen + L1 + sync loss {syncnet_wt}), bf16 operands / fp32 master+grads, B={B} x T={T} per GPU, "
                       f"{world} GPU(s), gradient all-reduce {'ncclAllReduce(avg) in 3 buckets overlapped with the backward' if world > 1 else 'n/a (1 GPU)'}",
             "ms_per_step": ms, "crops_per_s": world * B * T / ms * 1e3, "windows_per_s": world * B / ms * 1e3,
@@ -378,7 +386,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     if args.workload == "train":
         tb = 64 if args.batch == B_DEFAULT else args.batch
-        r = measure_train(dev, rank, world, args.steps, args.warmup, B=tb, T=args.frames)
+        r = measure_train(dev, rank, world, args.steps, args.warmup, B=tb, T=args.frames, profile_out=args.profile_out)
         if rank == 0:
             line = {"metric": "wav2lip_train.py iterations: 96x96 face-crops/sec trained (B=64/GPU, T=5, bf16)", "value": r["crops_per_s"],
                     "unit": "crops/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],

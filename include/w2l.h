@@ -256,6 +256,11 @@ int w2l_train_last_output(w2l_ctx* ctx, float* out_dev, int64_t n, void* stream)
 /* algorithmic forward FLOPs of the last training plan of `net` (2 x true MACs of its convs) */
 double w2l_train_flops(w2l_ctx* ctx, int net);
 
+/* Per-stage CUDA-event times of the last training plan of `net` (run one forward + backward first): rows
+ * "<block> fwd | bn | bwd_bn | dgrad | wgrad" with the stage's algorithmic FLOPs; returns the number of rows (<= cap). */
+int w2l_train_profile(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out, char (*names_out)[64],
+                      void* stream);
+
 /* Data-parallel training: the gradient all-reduce is the one collective of the system.  NCCL is
  * resolved at run time from the process (torch loads libnccl.so.2); rank 0 creates the 128-byte unique id, the host
  * side broadcasts it (torch.distributed), every rank calls w2l_comm_init.  w2l_wav2lip_train_step then averages the

@@ -31,7 +31,7 @@ EXPORTS = [
     "w2l_f16_overflow",
     "w2l_crop_resize_u8", "w2l_paste_u8", "w2l_lipsync_frames_u8",
     "w2l_train_bind", "w2l_train_forward", "w2l_train_backward", "w2l_adam_step", "w2l_wav2lip_train_step",
-    "w2l_train_last_output", "w2l_train_flops", "w2l_comm_unique_id", "w2l_comm_init", "w2l_conv_block_train",
+    "w2l_train_last_output", "w2l_train_flops", "w2l_comm_unique_id", "w2l_comm_init", "w2l_conv_block_train", "w2l_train_profile",
 ]
 
 
@@ -111,6 +111,7 @@ def get_lib() -> C.CDLL:
     lib.w2l_train_last_output.argtypes = [vp, vp, i64, vp]
     lib.w2l_train_flops.argtypes = [vp, i32]
     lib.w2l_train_flops.restype = C.c_double
+    lib.w2l_train_profile.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.w2l_comm_unique_id.argtypes = [vp, C.c_char_p]
     lib.w2l_comm_init.argtypes = [vp, C.c_char_p, i32, i32]
     lib.w2l_conv_block_train.argtypes = [vp, C.POINTER(LayerInfo), vp, i32, i32, i32] + [vp] * 14
@@ -188,6 +189,15 @@ class Context:
         arr_p = (C.c_void_p * n)(*[tensors[s][0] for s in names])
         arr_c = (C.c_int64 * n)(*[tensors[s][1] for s in names])
         check(self.lib.w2l_load_weights(self.h, net, n, arr_n, arr_p, arr_c, C.c_void_p(stream)))
+
+    def train_profile(self, net: int, iters: int = 3, stream: int = 0, cap: int = 512):
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        names = ((C.c_char * 64) * cap)()
+        k = self.lib.w2l_train_profile(self.h, net, iters, cap, ms, fl, names, C.c_void_p(stream))
+        if k < 0:
+            check(k)
+        return [(names[i].value.decode(), float(ms[i]), float(fl[i])) for i in range(k)]
 
     def profile_plan(self, net: int, iters: int = 5, stream: int = 0, cap: int = 256):
         ms = (C.c_float * cap)()

@@ -241,6 +241,27 @@ __global__ void pack_w_kernel(const PackParams p) {
     }
 }
 
+// All weight slabs of a training plan in ONE launch (the slabs are re-packed from the fp32 masters every step: ~240 jobs).
+// blk_job[b] = job of block b, blk_first[j] = first block of job j.
+template <bool kBF16>
+__global__ void pack_multi_kernel(const PackParams* jobs, const int* blk_job, const int* blk_first) {
+    const int j = blk_job[blockIdx.x];
+    const PackParams& p = jobs[j];
+    const long long total = (long long)p.ntaps * p.cout_pad * p.cin_pad;
+    const long long nblk = (total + 4095) / 4096;      // blocks of this job: 4096 elements each
+    const long long b = blockIdx.x - blk_first[j];
+    const long long end = (b + 1) * 4096 < total ? (b + 1) * 4096 : total;
+    (void)nblk;
+    for (long long i = b * 4096 + threadIdx.x; i < end; i += blockDim.x) {
+        const int ci = (int)(i % p.cin_pad);
+        const int co = (int)((i / p.cin_pad) % p.cout_pad);
+        const int t = (int)(i / ((long long)p.cin_pad * p.cout_pad));
+        float v = 0.0f;
+        if (ci < p.cin && co < p.cout) v = p.src[co * p.s_co + ci * p.s_ci + p.r[t] * p.s_r + p.s[t] * p.s_s];
+        p.dst[i] = to16<kBF16>(v);
+    }
+}
+
 // "kw folded into K" packing for the first layers (tiny Cin): dst[r][co][s*Cp + c] = w[co][c][r][s]
 struct PackFoldParams {
     const float* src;  // (cout, cin, kh, kw)

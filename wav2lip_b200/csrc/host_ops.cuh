@@ -351,7 +351,9 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
         const int EW = BN < 64 ? BN : 64;
         const CUtensorMapDataType dt = ctx->bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
         const CUtensorMapSwizzle esw = EW == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : EW == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
-        cuuint64_t dims[4] = {(cuuint64_t)a.cout, (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
+        // the channel extent is the destination view's: a launch may compute more (zero) channels than it stores (dgrad of
+        // the 80-channel output block runs as one 128-wide tile), the TMA store clips them
+        cuuint64_t dims[4] = {(cuuint64_t)std::min(a.cout, a.out.C), (cuuint64_t)a.Wl, (cuuint64_t)a.Hl, (cuuint64_t)a.in.N};
         cuuint32_t box[4] = {(cuuint32_t)EW, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bn};
         cuuint32_t es[4] = {1, 1, 1, 1};
         cuuint64_t os[3] = {(cuuint64_t)p.ep.out_sx * 2, (cuuint64_t)p.ep.out_sy * 2, (cuuint64_t)p.ep.out_sn * 2};
@@ -370,6 +372,7 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
         p.epi_box_bytes = (unsigned)(bw * bh * bn * EW * 2);
     }
     if (w.ntaps > kMaxTaps) return fail(W2L_EINVAL, "%s: too many taps", a.name.c_str());
+    if (a.cout > a.out.C && !p.tma_epi && !a.head) return fail(W2L_ESTATE, "%s: %d computed channels for a %d-channel destination need the TMA-store epilogue", a.name.c_str(), a.cout, a.out.C);
     if (ctx->x2) {
         // split operands: x*w ~= x_hi*w_hi + x_lo*w_hi + x_hi*w_lo (the dropped x_lo*w_lo term is ~2^-22 relative)
         if (a.in.lo_off <= 0 || w.nslabs != 2 * w.ntaps) return fail(W2L_ESTATE, "%s: split-operand mode needs hi/lo planes", a.name.c_str());

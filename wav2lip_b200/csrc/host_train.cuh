@@ -51,6 +51,7 @@ struct TrainPlan {
     std::vector<PackFoldParams> pack_fold_jobs;
     std::vector<FoldJob> fold_jobs;
     bool allow_fold = false, allow_rowstack = false;   // the context's own switches (the builder turns them off around itself)
+    PackParams* pack_dev = nullptr; int *pack_blk_job = nullptr, *pack_blk_first = nullptr; int pack_blocks = 0;   // one-launch repack
     std::vector<TBlock> blocks;    // forward order
     std::vector<size_t> ingest;    // indices of the ingest ops
     // generator
@@ -151,6 +152,9 @@ static Layer dgrad_layer(const Layer& L, int Hin, int Win, int Ho, int Wo) {
     } else if (L.sh == 1 && L.sw == 1) {       // stride-1 conv     ->  conv with flipped taps, pad k-1-p
         d.kind = W2L_BLOCK_CONV_PLAIN;
         d.ph = L.kh - 1 - L.ph; d.pw = L.kw - 1 - L.pw;
+        // 80 input channels (the output block) would tile as 5 x 16 output channels, each pass re-reading dz: compute 128
+        // (48 zero rows) in one pass instead; the TMA store clips at the real channel count
+        if (d.cout > 64 && d.cout % 64 != 0 && d.cout < 128) d.cout = 128;
     } else {                                   // strided conv      ->  transposed conv with the SAME tensor
         d.kind = W2L_BLOCK_CONVT_BN_RELU;
         d.out_pad = Hin - ((Ho - 1) * L.sh - 2 * L.ph + L.kh);   // rows the forward's floor division dropped (per axis: emit uses out dims)
@@ -169,14 +173,15 @@ static int load_dgrad_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const Laye
         return load_layer(ctx, lw, t, W, nullptr, nullptr, nullptr, nullptr, nullptr, false, false, st);
     }
     // stride 1: dst[tap][ci][co] = W[co][ci][r][s], tap (r,s) reads dz at (y + ph - r, x + pw - s)
+    // (Ld.cout may have been widened to a multiple of 128 — see dgrad_layer — the extra rows are zero and never stored)
     free_layer(*lw);
     std::vector<std::pair<int, int>> rs;
     PackedW pw;
     for (int r = 0; r < L.kh; ++r)
         for (int s = 0; s < L.kw; ++s) { rs.push_back({r, s}); pw.dy.push_back((signed char)(L.ph - r)); pw.dx.push_back((signed char)(L.pw - s)); }
-    CKR(pack_taps(ctx, &pw, W, L.cin, L.cout, L.kh, L.kw, true, rs, 16, st));
+    CKR(pack_taps(ctx, &pw, W, L.cin, L.cout, L.kh, L.kw, true, rs, Ld.cout, st));
     lw->ph.push_back(pw);
-    const int n_pad = round_up(L.cin, 16);
+    const int n_pad = Ld.cout;
     void* sc = nullptr; void* sh = nullptr;
     CKR(dev_alloc(&sc, (size_t)n_pad * 4));
     CKR(dev_alloc(&sh, (size_t)n_pad * 4));
@@ -564,11 +569,26 @@ static int get_train_plan(w2l_ctx* ctx, int net, int B, int T, bool want_wgrad, 
 // replay
 // ------------------------------------------------------------------------------------------------
 static int repack_weights(w2l_ctx* ctx, TrainPlan* tp, cudaStream_t st) {
-    for (const PackParams& pp : tp->pack_jobs) {
-        const size_t n = (size_t)pp.ntaps * pp.cout_pad * pp.cin_pad;
-        const int blocks = (int)std::min<size_t>((n + 255) / 256, 4096);
-        if (ctx->bf16) pack_w_kernel<true><<<blocks, 256, 0, st>>>(pp);
-        else pack_w_kernel<false><<<blocks, 256, 0, st>>>(pp);
+    if (!tp->pack_jobs.empty()) {
+        if (!tp->pack_dev) {   // job table + block map, built once per plan
+            std::vector<int> blk_job, blk_first;
+            for (size_t j = 0; j < tp->pack_jobs.size(); ++j) {
+                const PackParams& pp = tp->pack_jobs[j];
+                const long long total = (long long)pp.ntaps * pp.cout_pad * pp.cin_pad;
+                blk_first.push_back((int)blk_job.size());
+                for (long long b = 0; b < (total + 4095) / 4096; ++b) blk_job.push_back((int)j);
+            }
+            void* d = nullptr;
+            CKR(plan_alloc(&tp->pl, &d, tp->pack_jobs.size() * sizeof(PackParams))); tp->pack_dev = (PackParams*)d;
+            CKR(plan_alloc(&tp->pl, &d, blk_job.size() * 4)); tp->pack_blk_job = (int*)d;
+            CKR(plan_alloc(&tp->pl, &d, blk_first.size() * 4)); tp->pack_blk_first = (int*)d;
+            CK(cudaMemcpy(tp->pack_dev, tp->pack_jobs.data(), tp->pack_jobs.size() * sizeof(PackParams), cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(tp->pack_blk_job, blk_job.data(), blk_job.size() * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(tp->pack_blk_first, blk_first.data(), blk_first.size() * 4, cudaMemcpyHostToDevice));
+            tp->pack_blocks = (int)blk_job.size();
+        }
+        if (ctx->bf16) pack_multi_kernel<true><<<tp->pack_blocks, 256, 0, st>>>(tp->pack_dev, tp->pack_blk_job, tp->pack_blk_first);
+        else pack_multi_kernel<false><<<tp->pack_blocks, 256, 0, st>>>(tp->pack_dev, tp->pack_blk_job, tp->pack_blk_first);
         ctx->launches++;
     }
     for (const PackFoldParams& fp : tp->pack_fold_jobs) {

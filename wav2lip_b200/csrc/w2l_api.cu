@@ -809,6 +809,71 @@ double w2l_train_flops(w2l_ctx* ctx, int net) {
     return ctx->train->last[net]->fwd_flops;
 }
 
+
+/* Per-stage CUDA-event times of the last training plan of `net` (after a forward + backward have run, so every buffer holds
+ * real data): for each block "<name> fwd / stats+apply / bwd_bn / dgrad / wgrad", `iters` back-to-back repetitions each.
+ * Returns the number of rows written (<= cap). */
+int w2l_train_profile(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out, char (*names_out)[64], void* stream) {
+    if (!ctx || net < 0 || net > 2 || iters <= 0 || !ctx->train) return fail(W2L_EINVAL, "bad argument");
+    TrainPlan* tp = ctx->train->last[net];
+    if (!tp) return fail(W2L_ESTATE, "no training forward has run for net %d", net);
+    DeviceGuard g(ctx->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    int k = 0;
+    const bool pdl = ctx->use_pdl;
+    ctx->use_pdl = false;
+    auto timed = [&](const std::string& name, double flops, const std::function<int()>& fn) -> int {
+        if (k >= cap) return W2L_OK;
+        CKR(fn());
+        CK(cudaEventRecord(e0, st));
+        for (int i = 0; i < iters; ++i) CKR(fn());
+        CK(cudaEventRecord(e1, st));
+        CK(cudaEventSynchronize(e1));
+        float ms = 0;
+        CK(cudaEventElapsedTime(&ms, e0, e1));
+        if (ms_out) ms_out[k] = ms / iters;
+        if (flop_out) flop_out[k] = flops;
+        if (names_out) snprintf(names_out[k], 64, "%s", name.c_str());
+        ++k;
+        return W2L_OK;
+    };
+    int r = W2L_OK;
+    for (TBlock& b : tp->blocks) {
+        double f = 0;
+        for (size_t i = b.fwd0; i < b.fwd1; ++i) f += tp->pl.ops[i].flops;
+        // forward conv only, then the statistics + normalise passes (running averages untouched)
+        r = timed(b.L.name + " fwd", f, [&]() -> int { for (size_t i = b.fwd0; i < b.fwd1; ++i) CKR(launch_conv(ctx, tp->pl.ops[i], st)); return W2L_OK; });
+        if (r != W2L_OK) break;
+        if (b.bn) {
+            TBlock c = b; c.fwd0 = c.fwd1 = 0;
+            r = timed(b.L.name + " bn", 0, [&]() -> int { return block_forward(ctx, tp, c, false, st); });
+            if (r != W2L_OK) break;
+        }
+        {
+            TBlock c = b; c.dg0 = c.dg1 = 0; c.wg.on = false;
+            r = timed(b.L.name + " bwd_bn", 0, [&]() -> int { return block_backward(ctx, tp, c, false, false, st); });
+            if (r != W2L_OK) break;
+        }
+        if (b.dg1 > b.dg0) {
+            double fd = 0;
+            for (size_t i = b.dg0; i < b.dg1; ++i) fd += tp->pl.ops[i].flops;
+            r = timed(b.L.name + " dgrad", fd, [&]() -> int { for (size_t i = b.dg0; i < b.dg1; ++i) CKR(launch_conv(ctx, tp->pl.ops[i], st)); return W2L_OK; });
+            if (r != W2L_OK) break;
+        }
+        if (b.wg.on) {
+            r = timed(b.L.name + " wgrad", b.wg.flops, [&]() -> int { return launch_wgrad(ctx, tp, b, false, st); });
+            if (r != W2L_OK) break;
+        }
+    }
+    ctx->use_pdl = pdl;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return r == W2L_OK ? k : r;
+}
+
 /* One block, train mode, forward + backward (the operator-level entry of the per-geometry gradient tests):
  *   y = block(x) with batch statistics; given dy: dx, dw, db, dgamma, dbeta; running stats updated in place. */
 int w2l_conv_block_train(w2l_ctx* ctx, const w2l_layer_info* spec, const float* x, int N, int H, int W, float* weight, float* bias,

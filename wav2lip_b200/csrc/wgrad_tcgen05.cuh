@@ -257,7 +257,15 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReducePara
         if (n0 + n < p.Cn) {
             const float* src = p.ws + ((long long)t * p.Mp + m) * p.Np + n0 + n;
             const long long split_stride = (long long)p.ntaps * p.Mp * p.Np;
-            for (int k = 0; k < p.splits; ++k) s += __ldg(src + k * split_stride);
+            // four loads in flight per thread (the split loop is otherwise one dependent-latency chain per item)
+            float s0 = 0.0f, s1 = 0.0f, s2 = 0.0f, s3 = 0.0f;
+            int k = 0;
+            for (; k + 3 < p.splits; k += 4) {
+                s0 += __ldg(src + (k + 0) * split_stride); s1 += __ldg(src + (k + 1) * split_stride);
+                s2 += __ldg(src + (k + 2) * split_stride); s3 += __ldg(src + (k + 3) * split_stride);
+            }
+            for (; k < p.splits; ++k) s0 += __ldg(src + k * split_stride);
+            s = (s0 + s1) + (s2 + s3);
         }
         red_t[n * pitch + t] = s;
     }
