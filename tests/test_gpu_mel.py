@@ -78,3 +78,33 @@ def test_mel_shift_property():
     b = audio.melspectrogram(wav[2000:])
     # pre-emphasis makes sample 0 special and reflect padding touches 2 frames each side
     assert np.array_equal(a[:, 10 + 3:-3], b[:, 3:-3])
+
+
+def test_mel_both_kernels_agree():
+    """The register-resident FFT (mel_kernel_v2) and the shared-memory Stockham FFT (mel_kernel, W2L_DISABLE_MELV2=1): the
+    same arithmetic in a different order — both within 1e-4 of the oracle, and within 2e-5 of each other."""
+    from wav2lip_b200 import _lib
+    wav = M.make_wav(16000 * 4 + 321, seed=13, kind="mix")
+    ref = M.melspectrogram(wav)
+    x = torch.from_numpy(wav).cuda()
+    outs = []
+    for flag in (None, "1"):
+        old = os.environ.get("W2L_DISABLE_MELV2")
+        try:
+            if flag is None:
+                os.environ.pop("W2L_DISABLE_MELV2", None)
+            else:
+                os.environ["W2L_DISABLE_MELV2"] = flag
+            ctx = _lib.Context(0)
+        finally:
+            if old is None:
+                os.environ.pop("W2L_DISABLE_MELV2", None)
+            else:
+                os.environ["W2L_DISABLE_MELV2"] = old
+        out = torch.empty((80, 1 + x.numel() // 200), device="cuda")
+        import ctypes as C
+        _lib.check(ctx.lib.w2l_melspectrogram(ctx.h, C.c_void_p(x.data_ptr()), x.numel(), C.c_void_p(out.data_ptr()), None))
+        torch.cuda.synchronize()
+        outs.append(out.cpu().numpy())
+        assert np.abs(outs[-1] - ref).max() <= TOL
+    assert np.abs(outs[0] - outs[1]).max() <= 2e-5

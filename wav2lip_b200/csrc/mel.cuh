@@ -208,7 +208,7 @@ __device__ __forceinline__ double2 shfl_d2(double2 v, int src_lane) {
     return make_double2(__shfl_sync(0xffffffffu, v.x, src_lane, 16), __shfl_sync(0xffffffffu, v.y, src_lane, 16));
 }
 
-__global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams p) {
+__global__ void __launch_bounds__(MEL2_THREADS, 4) mel_kernel_v2(const MelParams p) {
     extern __shared__ uint8_t mel_smem[];
     double2* tw = reinterpret_cast<double2*>(mel_smem);                 // [401] exp(-2 pi i m / 800)  (+3 pad)
     double2* ybuf = tw + 404;                                            // [FPB][16][25]
@@ -223,8 +223,6 @@ __global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams
         const int f = tid / 25, n1 = tid % 25;
         const long long t = (long long)blockIdx.x * MEL2_FPB + f;
         if (t < p.F) {
-            const double2 ca = tw[2 * n1];       // (cos a, -sin a), a = 2 pi (2 n1) / 800   — also W400^n1
-            const double2 cb = tw[2 * n1 + 1];   // the odd sample of the pair
             double2 v[16];
             const long long base = t * MEL_HOP - MEL_NFFT / 2 + 2 * n1;
 #pragma unroll
@@ -246,9 +244,10 @@ __global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams
                     }
                     y0 = yy[0]; y1 = yy[1];
                 }
-                // periodic Hann: 0.5 - 0.5 cos(a + n2 pi/8),  cos(a + phi) = cos a cos phi - sin a sin phi,  sin a = -ca.y
-                const double c0 = ca.x * kMelC8[n2].x + ca.y * kMelC8[n2].y;
-                const double c1 = cb.x * kMelC8[n2].x + cb.y * kMelC8[n2].y;
+                // periodic Hann 0.5 - 0.5 cos(2 pi n / 800), n = 2 n1 + 50 n2 (+1), from the table (cos is even around 400)
+                const int n = 2 * n1 + 50 * n2;
+                const double c0 = tw[n <= 400 ? n : MEL_NFFT - n].x;
+                const double c1 = tw[n + 1 <= 400 ? n + 1 : MEL_NFFT - n - 1].x;
                 v[n2] = make_double2((0.5 - 0.5 * c0) * y0, (0.5 - 0.5 * c1) * y1);
             }
             // 16-point FFT over n2 = 4 a + b  ->  k2 = c + 4 d
@@ -260,7 +259,6 @@ __global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams
 #pragma unroll
                 for (int c = 0; c < 4; ++c) u[b][c] = (b * c == 0) ? q[c] : cmul(q[c], kMelW16[b * c]);
             }
-            double2 pw = make_double2(1.0, 0.0);
             double2 Y[16];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -272,9 +270,11 @@ __global__ void __launch_bounds__(MEL2_THREADS, 3) mel_kernel_v2(const MelParams
             double2* dst = ybuf + f * 400 + n1;
             dst[0] = Y[0];
 #pragma unroll
-            for (int k2 = 1; k2 < 16; ++k2) {      // W400^(n1 k2) by recurrence from W400^n1
-                pw = cmul(pw, ca);
-                dst[k2 * 25] = cmul(Y[k2], pw);
+            for (int k2 = 1; k2 < 16; ++k2) {      // W400^(n1 k2) = W800^(2 n1 k2 mod 800), upper half by conjugate symmetry
+                const int m = (2 * n1 * k2) % MEL_NFFT;
+                double2 w = tw[m <= 400 ? m : MEL_NFFT - m];
+                if (m > 400) w.y = -w.y;
+                dst[k2 * 25] = cmul(Y[k2], w);
             }
         }
     }
