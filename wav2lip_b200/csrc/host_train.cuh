@@ -226,9 +226,13 @@ constexpr int kWgSmemMax = 225 * 1024;
 static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need) {
     const Layer& L = b->L;
     const bool convT = L.kind == W2L_BLOCK_CONVT_BN_RELU;
-    const Act& S = convT ? b->x : b->dz;     // on the dense pixel grid of the sum
-    const Act& Tt = convT ? b->dz : b->x;    // read shifted / strided
-    const int Cm = convT ? L.cin : L.cout, Cn = convT ? L.cout : L.cin;
+    // A stride-1 conv is symmetric in its two tensors (sum over y,x of dz[y,x] x[y+d] == sum over y',x' of x[y',x'] dz[y'-d]):
+    // when the input is wide and the output narrow (the 80 -> 32 output block) put x on the M side and dz, with all its taps
+    // in one group, on the N side — one pass over the pixels instead of three
+    const bool swap = !convT && L.sh == 1 && L.sw == 1 && L.cin > 64 && L.cout <= 64;
+    const Act& S = (convT || swap) ? b->x : b->dz;     // on the dense pixel grid of the sum
+    const Act& Tt = (convT || swap) ? b->dz : b->x;    // read shifted / strided
+    const int Cm = (convT || swap) ? L.cin : L.cout, Cn = (convT || swap) ? L.cout : L.cin;
     WgradOp& w = b->wg;
     w.on = true;
     const int cn_pad = Tt.C;                 // channels of the view (first layers: padded to 16)
@@ -243,7 +247,10 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     p.tg = (p.ntaps + p.ngroups - 1) / p.ngroups;
     p.ngroups = (p.ntaps + p.tg - 1) / p.tg;
     for (int r = 0; r < L.kh; ++r)
-        for (int s = 0; s < L.kw; ++s) { p.dy[r * L.kw + s] = (signed char)(r - L.ph); p.dx[r * L.kw + s] = (signed char)(s - L.pw); }
+        for (int s = 0; s < L.kw; ++s) {
+            p.dy[r * L.kw + s] = (signed char)(swap ? L.ph - r : r - L.ph);
+            p.dx[r * L.kw + s] = (signed char)(swap ? L.pw - s : s - L.pw);
+        }
     p.sx = L.sw; p.sy = L.sh;
     // pixels per chunk: at least three pipeline stages must fit
     int maxP = (kWgSmemMax - 1024) / 3 / (256 + p.tg * BN * 2) / 16 * 16;
@@ -273,6 +280,7 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     w.grid = (int)std::min<long long>(base_units * p.splits, ctx->num_sms);
     WgradReduceParams& r = w.rp;
     r.ws = nullptr; r.out = b->gW; r.splits = p.splits; r.ntaps = p.ntaps; r.Cm = Cm; r.Cn = Cn; r.Mp = Mp; r.Np = Np; r.accumulate = 0;
+    r.transpose = swap ? 1 : 0;
     w.flops = 2.0 * (double)L.cin * L.cout * L.kh * L.kw * (double)S.N * S.H * S.W;
     return W2L_OK;
 }
@@ -358,7 +366,7 @@ static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const L
     b.nblk = (int)std::max<long long>(1, std::min<long long>((b.M + rows - 1) / rows, (long long)ctx->num_sms * 4));
     void* p = nullptr;
     CKR(plan_alloc(&tp->pl, &p, (size_t)b.nblk * 2 * L.cout * 4)); b.partial = (float*)p;
-    CKR(plan_alloc(&tp->pl, &p, (size_t)2 * L.cout * 4)); b.stats = (float*)p;
+    CKR(plan_alloc(&tp->pl, &p, (size_t)4 * L.cout * 4)); b.stats = (float*)p;   // mean, invstd, G, H
     CKR(plan_alloc(&tp->pl, &p, (size_t)3 * L.cout * 4)); b.coef = (float*)p;
     // ---- backward ----
     CKR(tp_act(tp, &b.dz, y.N, y.H, y.W, L.cout));
@@ -645,15 +653,15 @@ static int block_forward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool update_run
     rp.z = b.z.ptr(); rp.z_pitch = b.z.Cs; rp.partial = b.partial; rp.M = b.M; rp.C = C;
     launch_chan_reduce<0>(ctx, rp, b.nblk, st);
     bn_finalize_kernel<<<(C + 31) / 32, kFinThreads, 0, st>>>(b.partial, b.nblk, C, (double)b.M, b.b, update_running ? b.rmean : nullptr,
-                                                       update_running ? b.rvar : nullptr, b.stats);
+                                                       update_running ? b.rvar : nullptr, b.gamma, b.beta, b.stats);
     ctx->launches++;
     BnApplyParams ap;
     memset(&ap, 0, sizeof(ap));
     ap.z = b.z.ptr(); ap.z_pitch = b.z.Cs;
     if (b.L.residual) { ap.res = b.x.ptr(); ap.res_pitch = b.x.Cs; }
     ap.y = b.y.ptr(); ap.y_pitch = b.y.Cs; ap.y_f32 = b.y_f32;
-    ap.stats = b.stats; ap.gamma = b.gamma; ap.beta = b.beta; ap.M = b.M; ap.C = C;
-    const int grid = elem_grid(ctx, b.M * (C / 8));
+    ap.stats = b.stats; ap.M = b.M; ap.C = C;
+    const int grid = b.nblk * 2;   // rows-of-pixels layout (kBnThreads / (C/8) pixels per block iteration), as the reductions
     if (ctx->bf16) bn_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(ap);
     else bn_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(ap);
     ctx->launches++;
@@ -666,7 +674,11 @@ static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bo
     memset(&rp, 0, sizeof(rp));
     rp.dy = b.dy.ptr(); rp.dy_pitch = b.dy.Cs; rp.y = b.y.ptr(); rp.y_pitch = b.y.Cs;
     rp.partial = b.partial; rp.M = b.M; rp.C = C;
+    // non-residual BatchNorm blocks: y > 0  <=>  gamma * zhat + beta > 0 (the value the forward rounded to bf16 has the same
+    // sign unless it underflows): recompute the mask from z instead of reading y a second and third time
+    const bool mask_from_z = b.bn && !b.L.residual;
     if (b.bn) {
+        if (mask_from_z) rp.y = nullptr;
         rp.z = b.z.ptr(); rp.z_pitch = b.z.Cs; rp.stats = b.stats;
         launch_chan_reduce<1>(ctx, rp, b.nblk, st);
         const bool pg = wgrad && b.ggamma;
@@ -677,7 +689,8 @@ static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bo
         memset(&ap, 0, sizeof(ap));
         ap.z = b.z.ptr(); ap.z_pitch = b.z.Cs; ap.dy = b.dy.ptr(); ap.dy_pitch = b.dy.Cs; ap.y = b.y.ptr(); ap.y_pitch = b.y.Cs;
         ap.dz = b.dz.ptr(); ap.du = b.L.residual ? b.du.ptr() : nullptr; ap.stats = b.stats; ap.coef = b.coef; ap.M = b.M; ap.C = C;
-        const int grid = elem_grid(ctx, b.M * (C / 8));
+        if (mask_from_z) ap.y = nullptr;
+        const int grid = b.nblk * 2;
         if (ctx->bf16) bn_bwd_apply_kernel<true><<<grid, kBnThreads, 0, st>>>(ap);
         else bn_bwd_apply_kernel<false><<<grid, kBnThreads, 0, st>>>(ap);
         ctx->launches++;

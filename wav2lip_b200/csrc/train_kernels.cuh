@@ -48,7 +48,9 @@ struct ChanReduceParams {
     const uint16_t* dy; long long dy_pitch;  // modes 1, 2
     const uint16_t* y; long long y_pitch;    // modes 1, 2
     uint16_t* dz; long long dz_pitch;        // mode 2 output
-    const float* stats;                      // mode 1: [2][C] mean, invstd
+    const float* stats;                      // mode 1: [4][C] mean, invstd, G = gamma * invstd, H = beta - mean * G
+                                             // with y == nullptr (non-residual block) the ReLU mask is recomputed as
+                                             // G z + H > 0 instead of re-reading y (one tensor pass less)
     float* partial;                          // [gridDim.x][2][C]
     long long M;                             // pixels
     int C;
@@ -63,10 +65,10 @@ __global__ void __launch_bounds__(kBnThreads) chan_reduce_kernel(const ChanReduc
     float s0[8], s1[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.0f;
-    float mean[8], istd[8];
-    if (MODE == 1 && r < rows) {
+    float G[8], H[8];
+    if (MODE == 1 && r < rows && p.y == nullptr) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { mean[j] = p.stats[g * 8 + j]; istd[j] = p.stats[p.C + g * 8 + j]; }
+        for (int j = 0; j < 8; ++j) { G[j] = p.stats[2 * p.C + g * 8 + j]; H[j] = p.stats[3 * p.C + g * 8 + j]; }
     }
     if (r < rows) {
         for (long long pix = (long long)blockIdx.x * rows + r; pix < p.M; pix += (long long)gridDim.x * rows) {
@@ -78,14 +80,15 @@ __global__ void __launch_bounds__(kBnThreads) chan_reduce_kernel(const ChanReduc
             } else {
                 float d[8], yv[8];
                 unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.dy + pix * p.dy_pitch) + g), d);
-                unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch) + g), yv);
+                if (MODE != 1 || p.y != nullptr) unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch) + g), yv);
                 if (MODE == 1) {
                     unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.z + pix * p.z_pitch) + g), a);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float du = yv[j] > 0.0f ? d[j] : 0.0f;
+                    for (int j = 0; j < 8; ++j) {   // sum du and sum du * z; the finalize kernel turns the latter into sum du * zhat
+                        const bool on = p.y != nullptr ? yv[j] > 0.0f : fmaf(G[j], a[j], H[j]) > 0.0f;
+                        const float du = on ? d[j] : 0.0f;
                         s0[j] += du;
-                        s1[j] = fmaf(du, (a[j] - mean[j]) * istd[j], s1[j]);
+                        s1[j] = fmaf(du, a[j], s1[j]);
                     }
                 } else {
 #pragma unroll
@@ -134,7 +137,7 @@ __device__ __forceinline__ void sum_partials_2(const float* partial, int nblk, i
 // unbiased variance).  The conv bias never enters the conv kernel in train mode (BatchNorm removes any per-channel
 // constant): it only shifts the batch mean, so it is added here, for running_mean.   grid = ceil(C / 32), block = 1024.
 __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* partial, int nblk, int C, double m, const float* bias, float* rmean,
-                                                                  float* rvar, float* stats) {
+                                                                  float* rvar, const float* gamma, const float* beta, float* stats) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
     sum_partials_2(partial, nblk, C, c, c < C, &s, &q);
@@ -142,8 +145,14 @@ __global__ void __launch_bounds__(kFinThreads) bn_finalize_kernel(const float* p
     const double mean = s / m;
     double var = q / m - mean * mean;
     if (var < 0.0) var = 0.0;
+    const float istd = (float)(1.0 / sqrt(var + (double)kBnEps));
     stats[c] = (float)mean;
-    stats[C + c] = (float)(1.0 / sqrt(var + (double)kBnEps));
+    stats[C + c] = istd;
+    if (gamma) {   // y = relu(G z + H [+ x])
+        const float G = gamma[c] * istd;
+        stats[2 * C + c] = G;
+        stats[3 * C + c] = beta[c] - (float)mean * G;
+    }
     if (rmean) rmean[c] = (1.0f - kBnMomentum) * rmean[c] + kBnMomentum * (float)(mean + (bias ? (double)bias[c] : 0.0));
     if (rvar) rvar[c] = (1.0f - kBnMomentum) * rvar[c] + kBnMomentum * (float)(m > 1.0 ? var * m / (m - 1.0) : var);
 }
@@ -154,24 +163,26 @@ struct BnApplyParams {
     const uint16_t* res; long long res_pitch;   // nullptr = no residual
     uint16_t* y; long long y_pitch;
     float* y_f32;                               // nullptr or dense [M][C]
-    const float* stats; const float* gamma; const float* beta;
+    const float* stats;                         // [4][C]: mean, invstd, G, H
     long long M; int C;
 };
 
+// Thread layout as in chan_reduce_kernel: thread = (pixel row r, channel group g); the per-channel constants of the
+// thread's 8 channels live in registers for the whole pixel loop (no per-element table loads).
 template <bool kBF16>
 __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnApplyParams p) {
     const int tpr = p.C >> 3;
-    const long long total = p.M * tpr;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / tpr;
-        const int g = (int)(i % tpr);
+    const int rows = kBnThreads / tpr;
+    const int g = threadIdx.x % tpr, r = threadIdx.x / tpr;
+    if (r >= rows) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { sc[j] = p.stats[2 * p.C + g * 8 + j]; sh[j] = p.stats[3 * p.C + g * 8 + j]; }   // G, H
+    for (long long pix = (long long)blockIdx.x * rows + r; pix < p.M; pix += (long long)gridDim.x * rows) {
         float a[8], o[8];
         unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.z + pix * p.z_pitch) + g), a);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int c = g * 8 + j;
-            o[j] = fmaf(__ldg(p.gamma + c), (a[j] - __ldg(p.stats + c)) * __ldg(p.stats + p.C + c), __ldg(p.beta + c));
-        }
+        for (int j = 0; j < 8; ++j) o[j] = fmaf(a[j], sc[j], sh[j]);
         if (p.res) {
             float rr[8];
             unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch) + g), rr);
@@ -190,18 +201,23 @@ __global__ void __launch_bounds__(kBnThreads) bn_apply_kernel(const BnApplyParam
 }
 
 // BatchNorm backward, second half: per-channel sums -> dgamma, dbeta and the three coefficients of
-//   dz = c1 * (du - c2 - zhat * c3),   c1 = gamma * invstd, c2 = mean(du), c3 = mean(du * zhat).
+//   dz = c1 * (du - c2 - zhat * c3) = P du + Q z + R,   c1 = gamma * invstd, c2 = mean(du), c3 = mean(du * zhat).
 __global__ void __launch_bounds__(kFinThreads) bn_bwd_finalize_kernel(const float* partial, int nblk, int C, double m, const float* gamma,
                                                                       const float* stats, float* dgamma, float* dbeta, int accumulate, float* coef) {
     const int c = blockIdx.x * 32 + (threadIdx.x & 31);
     double s, q;
-    sum_partials_2(partial, nblk, C, c, c < C, &s, &q);
+    sum_partials_2(partial, nblk, C, c, c < C, &s, &q);      // s = sum du, q = sum du * z
     if ((threadIdx.x >> 5) != 0 || c >= C) return;
+    const double mean = stats[c], istd = stats[C + c];
+    const double dg = istd * (q - mean * s);                 // sum du * zhat
     if (dbeta) dbeta[c] = accumulate ? dbeta[c] + (float)s : (float)s;
-    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)q : (float)q;
-    coef[c] = gamma[c] * stats[C + c];
-    coef[C + c] = (float)(s / m);
-    coef[2 * C + c] = (float)(q / m);
+    if (dgamma) dgamma[c] = accumulate ? dgamma[c] + (float)dg : (float)dg;
+    // dz = c1 (du - c2 - zhat c3), c1 = gamma istd, c2 = s/m, c3 = dg/m, zhat = istd z - mean istd
+    //    = P du + Q z + R
+    const double c1 = (double)gamma[c] * istd, c2 = s / m, c3 = dg / m;
+    coef[c] = (float)c1;
+    coef[C + c] = (float)(-c1 * c3 * istd);
+    coef[2 * C + c] = (float)(c1 * c3 * mean * istd - c1 * c2);
 }
 
 struct BnBwdApplyParams {
@@ -210,27 +226,34 @@ struct BnBwdApplyParams {
     const uint16_t* y; long long y_pitch;
     uint16_t* dz;          // dense [M][C]
     uint16_t* du;          // dense [M][C] or nullptr: gradient of the residual branch (conv.py:16-18: joins before the ReLU)
-    const float* stats; const float* coef;
-    long long M; int C;
+    const float* stats; const float* coef;   // stats [4][C] (mean, invstd, G, H), coef [3][C] (P, Q, R)
+    long long M; int C;                      // y == nullptr (non-residual block): mask from G z + H > 0
 };
 
 template <bool kBF16>
-__global__ void __launch_bounds__(kBnThreads) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
+__global__ void __launch_bounds__(kBnThreads, 4) bn_bwd_apply_kernel(const BnBwdApplyParams p) {
     const int tpr = p.C >> 3;
-    const long long total = p.M * tpr;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        const long long pix = i / tpr;
-        const int g = (int)(i % tpr);
+    const int rows = kBnThreads / tpr;
+    const int g = threadIdx.x % tpr, r = threadIdx.x / tpr;
+    if (r >= rows) return;
+    const bool from_z = p.y == nullptr;
+    float P[8], Q[8], R[8], G[8], H[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = g * 8 + j;
+        P[j] = p.coef[c]; Q[j] = p.coef[p.C + c]; R[j] = p.coef[2 * p.C + c];
+        G[j] = from_z ? p.stats[2 * p.C + c] : 0.0f; H[j] = from_z ? p.stats[3 * p.C + c] : 0.0f;
+    }
+    for (long long pix = (long long)blockIdx.x * rows + r; pix < p.M; pix += (long long)gridDim.x * rows) {
         float a[8], d[8], yv[8], o[8];
         unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.z + pix * p.z_pitch) + g), a);
         unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.dy + pix * p.dy_pitch) + g), d);
-        unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch) + g), yv);
+        if (!from_z) unpack8<kBF16>(__ldg(reinterpret_cast<const uint4*>(p.y + pix * p.y_pitch) + g), yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const int c = g * 8 + j;
-            d[j] = yv[j] > 0.0f ? d[j] : 0.0f;
-            const float zh = (a[j] - __ldg(p.stats + c)) * __ldg(p.stats + p.C + c);
-            o[j] = __ldg(p.coef + c) * (d[j] - __ldg(p.coef + p.C + c) - zh * __ldg(p.coef + 2 * p.C + c));
+            const bool on = from_z ? fmaf(G[j], a[j], H[j]) > 0.0f : yv[j] > 0.0f;
+            d[j] = on ? d[j] : 0.0f;
+            o[j] = fmaf(P[j], d[j], fmaf(Q[j], a[j], R[j]));
         }
         *(reinterpret_cast<uint4*>(p.dz + pix * p.C) + g) = pack8<kBF16>(o);
         if (p.du) *(reinterpret_cast<uint4*>(p.du + pix * p.C) + g) = pack8<kBF16>(d);

@@ -241,6 +241,7 @@ struct WgradReduceParams {
     int splits, ntaps, Cm, Cn;
     long long Mp, Np;
     int accumulate;
+    int transpose;   // 1: the parameter layout is [n][m][tap] (a conv whose operand roles were swapped: m = ci, n = co)
 };
 
 // grid = (ceil(Cn / 64), Cm), block = 256: a block sums the splits of one row m, 64 columns n, all taps — reading the
@@ -271,11 +272,12 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReducePara
     }
     __syncthreads();
     const int ncols = min(64, p.Cn - n0);
-    float* out = p.out + ((long long)m * p.Cn + n0) * p.ntaps;
     for (int i = threadIdx.x; i < ncols * p.ntaps; i += 256) {
         const int n = i / p.ntaps, t = i - n * p.ntaps;
         const float v = red_t[n * pitch + t];
-        out[i] = p.accumulate ? out[i] + v : v;
+        float* o = p.transpose ? p.out + ((long long)(n0 + n) * p.Cm + m) * p.ntaps + t
+                               : p.out + ((long long)m * p.Cn + n0) * p.ntaps + i;
+        *o = p.accumulate ? *o + v : v;
     }
 }
 
