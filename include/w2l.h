@@ -42,12 +42,14 @@ extern "C" {
 #define W2L_NET_GENERATOR 0   /* models.Wav2Lip            /root/reference/models/wav2lip.py:8-125   */
 #define W2L_NET_SYNCNET   1   /* models.SyncNet_color      /root/reference/models/syncnet.py:7-66    */
 #define W2L_NET_DISC      2   /* models.Wav2Lip_disc_qual  /root/reference/models/wav2lip.py:127-184 */
+#define W2L_NET_S3FD      3   /* face_detection s3fd       /root/reference/face_detection/detection/sfd/net_s3fd.py:22-129 */
 
 /* block kinds — /root/reference/models/conv.py */
 #define W2L_BLOCK_CONV_BN_RELU   0   /* Conv2d           conv.py:5-19  */
 #define W2L_BLOCK_CONVT_BN_RELU  1   /* Conv2dTranspose  conv.py:33-44 */
 #define W2L_BLOCK_CONV_LRELU     2   /* nonorm_Conv2d    conv.py:21-31 */
-#define W2L_BLOCK_CONV_PLAIN     3   /* bare nn.Conv2d heads: wav2lip.py:84, :152 (followed by Sigmoid) */
+#define W2L_BLOCK_CONV_PLAIN     3   /* bare nn.Conv2d heads: wav2lip.py:84, :152 (followed by Sigmoid); S3FD's mbox convs */
+#define W2L_BLOCK_CONV_RELU      4   /* F.relu(nn.Conv2d(x)): the S3FD backbone, net_s3fd.py:72-106 */
 
 /* operand precision of the tensor-core path (accumulation is always fp32) */
 #define W2L_PREC_F16  0   /* fp16 operands: 10-bit mantissa, same as TF32 (default) */
@@ -66,6 +68,7 @@ typedef struct w2l_layer_info {
     int32_t kh, kw, sh, sw, ph, pw;
     int32_t out_pad;    /* ConvTranspose2d output_padding */
     int32_t residual;   /* conv.py:16-18 */
+    int32_t cout_real;  /* 0, or the parameter tensor's real output-channel count when `cout` is its 16-padded width (S3FD heads) */
 } w2l_layer_info;
 
 /* ---- introspection (host only; usable without a GPU) ---- */
@@ -136,6 +139,17 @@ int w2l_paste_u8(w2l_ctx* ctx, const uint8_t* pred_dev, const uint8_t* frames_de
                  const int32_t* boxes_host, int N, uint8_t* out_frames_dev, void* stream);
 int w2l_lipsync_frames_u8(w2l_ctx* ctx, const float* mel_dev, const uint8_t* frames_dev, int F, int H, int W,
                           const int32_t* boxes_host, int N, uint8_t* out_frames_dev, void* stream);
+
+/* Scope row (f4): the S3FD face detector's network (face_detection/detection/sfd/net_s3fd.py:22-129), the per-frame GPU
+ * work of inference.py's face_detect (:73-100): 19 conv+ReLU layers (VGG16 backbone + fc6/fc7 + conv6/7), 5 max-pools,
+ * 3 L2Norm layers and the 12 mbox heads, max-out of the first scale's background logits included.
+ *   img (B,3,H,W) fp32, BGR minus (104,117,123) as detect.py:21-23 / :60-61 prepare it  ->  12 maps
+ *   outs[2i] = cls_i (B,2,h_i,w_i), outs[2i+1] = reg_i (B,4,h_i,w_i), i = 0..5 (strides 4..128), raw logits as the module
+ *   returns them (softmax / threshold / decode / NMS of detect.py:31-56 and bbox.py:44-64 stay on the host side).
+ * w2l_s3fd_out_dims writes the six (h_i, w_i) pairs for an H x W input.  Weights: w2l_load_weights(ctx, W2L_NET_S3FD, ...)
+ * with the module's own state_dict names ("conv1_1.weight", ..., "conv3_3_norm.weight", "conv7_2_mbox_loc.bias"). */
+int w2l_s3fd_out_dims(int H, int W, int32_t* dims12);
+int w2l_s3fd_forward(w2l_ctx* ctx, const float* img_dev, float* const* outs12_dev, int B, int H, int W, void* stream);
 
 /* Replaces `SyncNet_color.forward(audio, face)` (syncnet.py:55-66):
  *   mel (B,1,80,16), face (B,15,48,96) -> audio_emb (B,512), face_emb (B,512), both L2-normalised. */

@@ -13,8 +13,8 @@ from typing import Optional
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 W2L_OK, W2L_EINVAL, W2L_ENODEV, W2L_ECUDA, W2L_ENOMEM, W2L_ESTATE = 0, -1, -2, -3, -4, -5
-NET_GENERATOR, NET_SYNCNET, NET_DISC = 0, 1, 2
-BLOCK_CONV_BN_RELU, BLOCK_CONVT_BN_RELU, BLOCK_CONV_LRELU, BLOCK_CONV_PLAIN = 0, 1, 2, 3
+NET_GENERATOR, NET_SYNCNET, NET_DISC, NET_S3FD = 0, 1, 2, 3
+BLOCK_CONV_BN_RELU, BLOCK_CONVT_BN_RELU, BLOCK_CONV_LRELU, BLOCK_CONV_PLAIN, BLOCK_CONV_RELU = 0, 1, 2, 3, 4
 PREC_F16, PREC_BF16, PREC_F32X = 0, 1, 2
 TRAIN_WGRAD, TRAIN_ACCUMULATE, TRAIN_INPUT_GRAD, TRAIN_NO_STAT_UPDATE = 1, 2, 4, 8
 
@@ -29,7 +29,7 @@ EXPORTS = [
     "w2l_melspectrogram", "w2l_melspectrogram_host", "w2l_mel_num_frames", "w2l_mel_num_chunks", "w2l_mel_chunks",
     "w2l_set_debug", "w2l_mel_basis_host", "w2l_launch_count", "w2l_device_bytes", "w2l_profile_plan",
     "w2l_f16_overflow",
-    "w2l_crop_resize_u8", "w2l_paste_u8", "w2l_lipsync_frames_u8",
+    "w2l_crop_resize_u8", "w2l_paste_u8", "w2l_lipsync_frames_u8", "w2l_s3fd_out_dims", "w2l_s3fd_forward",
     "w2l_train_bind", "w2l_train_forward", "w2l_train_backward", "w2l_adam_step", "w2l_wav2lip_train_step",
     "w2l_train_last_output", "w2l_train_flops", "w2l_comm_unique_id", "w2l_comm_init", "w2l_conv_block_train", "w2l_train_profile",
 ]
@@ -42,7 +42,7 @@ class W2LError(RuntimeError):
 class LayerInfo(C.Structure):
     _fields_ = [("name", C.c_char * 64), ("kind", C.c_int32), ("cin", C.c_int32), ("cout", C.c_int32),
                 ("kh", C.c_int32), ("kw", C.c_int32), ("sh", C.c_int32), ("sw", C.c_int32),
-                ("ph", C.c_int32), ("pw", C.c_int32), ("out_pad", C.c_int32), ("residual", C.c_int32)]
+                ("ph", C.c_int32), ("pw", C.c_int32), ("out_pad", C.c_int32), ("residual", C.c_int32), ("cout_real", C.c_int32)]
 
 
 def lib_path() -> str:
@@ -100,6 +100,8 @@ def get_lib() -> C.CDLL:
     lib.w2l_profile_plan.argtypes = [vp, i32, i32, i32, vp, vp, vp, vp]
     lib.w2l_f16_overflow.argtypes = [vp, i32, C.POINTER(i32), vp]
     f32 = C.c_float
+    lib.w2l_s3fd_out_dims.argtypes = [i32, i32, C.POINTER(i32)]
+    lib.w2l_s3fd_forward.argtypes = [vp, vp, C.POINTER(vp), i32, i32, i32, vp]
     lib.w2l_crop_resize_u8.argtypes = [vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
     lib.w2l_paste_u8.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
     lib.w2l_lipsync_frames_u8.argtypes = [vp, vp, vp, i32, i32, i32, C.POINTER(i32), i32, vp, vp]
@@ -141,7 +143,7 @@ def net_layers(net: int):
         check(lib.w2l_net_layer_info(net, i, C.byref(li)))
         out.append({"name": li.name.decode(), "kind": li.kind, "cin": li.cin, "cout": li.cout,
                     "k": (li.kh, li.kw), "stride": (li.sh, li.sw), "pad": (li.ph, li.pw),
-                    "out_pad": li.out_pad, "residual": bool(li.residual)})
+                    "out_pad": li.out_pad, "residual": bool(li.residual), "cout_real": li.cout_real})
     return out
 
 

@@ -339,6 +339,62 @@ __global__ void disc_head_kernel(const uint16_t* x, const float* w, const float*
     if (lane == 0) prob[row] = 1.0f / (1.0f + __expf(-(s + b[0])));
 }
 
+// ---- S3FD (face_detection/detection/sfd/net_s3fd.py) glue kernels ---------------------------------------------------------
+// F.max_pool2d(h, 2, 2) (net_s3fd.py:74,78,84,90,96): NHWC 16-bit, floor semantics, 8 channels per thread
+template <bool kBF16>
+__global__ void maxpool2_kernel(const uint16_t* in, uint16_t* out, int N, int H, int W, int C) {
+    const int Ho = H >> 1, Wo = W >> 1, cg = C >> 3;
+    const long long total = (long long)N * Ho * Wo * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const int x = (int)((i / cg) % Wo), y = (int)((i / ((long long)cg * Wo)) % Ho), n = (int)(i / ((long long)cg * Wo * Ho));
+        const uint16_t* p = in + ((((long long)n * H + 2 * y) * W + 2 * x) * C) + g * 8;
+        const uint4 q[4] = {__ldg(reinterpret_cast<const uint4*>(p)), __ldg(reinterpret_cast<const uint4*>(p + C)),
+                            __ldg(reinterpret_cast<const uint4*>(p + (long long)W * C)), __ldg(reinterpret_cast<const uint4*>(p + (long long)W * C + C))};
+        uint16_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float m = -3.4e38f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t w = (&q[k].x)[j >> 1];
+                m = fmaxf(m, from16<kBF16>((uint16_t)((j & 1) ? (w >> 16) : (w & 0xFFFFu))));
+            }
+            o[j] = to16<kBF16>(m);
+        }
+        uint4 r;
+        r.x = o[0] | ((uint32_t)o[1] << 16); r.y = o[2] | ((uint32_t)o[3] << 16);
+        r.z = o[4] | ((uint32_t)o[5] << 16); r.w = o[6] | ((uint32_t)o[7] << 16);
+        *reinterpret_cast<uint4*>(out + ((((long long)n * Ho + y) * Wo + x) * C) + g * 8) = r;
+    }
+}
+
+// L2Norm (net_s3fd.py:6-19): x / (sqrt(sum_c x^2) + 1e-10) * weight[c]; one warp per pixel
+template <bool kBF16>
+__global__ void chan_l2norm_kernel(const uint16_t* in, uint16_t* out, const float* weight, long long pixels, int C) {
+    const long long pix = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (pix >= pixels) return;
+    const uint16_t* p = in + pix * C;
+    float s = 0.0f;
+    for (int c = lane; c < C; c += 32) { const float v = from16<kBF16>(p[c]); s = fmaf(v, v, s); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float inv = 1.0f / (sqrtf(s) + 1e-10f);
+    for (int c = lane; c < C; c += 32) out[pix * C + c] = to16<kBF16>(from16<kBF16>(p[c]) * inv * __ldg(weight + c));
+}
+
+// mbox head (fp32 NHWC, 16-channel pitch) -> the module's NCHW fp32 output; maxout: cls1 = [max(c0,c1,c2), c3] (net_s3fd.py:123-126)
+__global__ void s3fd_export_kernel(const float* in, float* out, int N, int H, int W, int Cout, int maxout) {
+    const long long total = (long long)N * Cout * H * W;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W), y = (int)((i / W) % H);
+        const int c = (int)((i / ((long long)W * H)) % Cout), n = (int)(i / ((long long)W * H * Cout));
+        const float* p = in + (((long long)n * H + y) * W + x) * 16;
+        out[i] = maxout ? (c == 0 ? fmaxf(fmaxf(p[0], p[1]), p[2]) : p[3]) : p[c];
+    }
+}
+
 // ---- evaluation-loop losses (wav2lip_train.py:178-198, 262-292; color_syncnet_train.py:133-138) -------------------------
 // cosine_loss: d = F.cosine_similarity(a, v) (eps 1e-8), loss = nn.BCELoss()(d.unsqueeze(1), y) — mean over the batch,
 // log terms clamped at -100 as torch does.  One warp per row, per-row terms to `terms`, then a single block sums them in

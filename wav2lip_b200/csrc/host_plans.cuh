@@ -208,9 +208,82 @@ static int build_disc_plan(w2l_ctx* ctx, Plan* pl) {
     return W2L_OK;
 }
 
-static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
-    char key[64];
-    snprintf(key, sizeof(key), "%d:%d:%d:%d", net, B, T, (int)ctx->keep_all);
+
+// face_detection/detection/sfd/net_s3fd.py:71-128: backbone with taps, L2Norm on the first three, two 3x3 heads per tap.
+static void s3fd_dims(int H, int W, int hs[6], int ws[6]) {
+    int h = H, w = W;
+    h /= 2; w /= 2; h /= 2; w /= 2;          // pool1, pool2 -> conv3_x
+    hs[0] = h; ws[0] = w;
+    h /= 2; w /= 2; hs[1] = h; ws[1] = w;    // conv4_x
+    h /= 2; w /= 2; hs[2] = h; ws[2] = w;    // conv5_x
+    h /= 2; w /= 2;                          // pool5
+    h += 4; w += 4; hs[3] = h; ws[3] = w;    // fc6: kernel 3, padding 3
+    h = (h + 2 - 3) / 2 + 1; w = (w + 2 - 3) / 2 + 1; hs[4] = h; ws[4] = w;   // conv6_2, stride 2
+    h = (h + 2 - 3) / 2 + 1; w = (w + 2 - 3) / 2 + 1; hs[5] = h; ws[5] = w;   // conv7_2
+}
+
+static int build_s3fd_plan(w2l_ctx* ctx, Plan* pl) {
+    const S3fdSpec& sp = s3fd_spec();
+    const NetW& nw = ctx->nets[W2L_NET_S3FD];
+    const int N = pl->N, H = pl->H, W = pl->W;
+    if (H < 32 || W < 32) return fail(W2L_EINVAL, "S3FD needs an image of at least 32 x 32 (five 2x2 pools)");
+    Act x;
+    CKR(plan_input_act(pl, &x, N, H, W, 3, nw.layers[0], sp.layers[0]));
+    add_ingest(pl, "ingest.img", 0, x, N, 3, (long long)3 * H * W, (long long)H * W, 0, 0, W);
+    auto conv = [&](int li, const Act& in, Act* out, bool f32 = false) -> int {
+        const Layer& L = sp.layers[li];
+        int Ho, Wo;
+        conv_out_dims(L, in.H, in.W, &Ho, &Wo);
+        CKR(plan_act(pl, out, N, Ho, Wo, L.cout, f32));
+        CKR(emit_block(ctx, pl, nw, li, L, in, *out, nullptr));
+        pl->layer_out[li] = *out;
+        return W2L_OK;
+    };
+    auto pool = [&](const Act& in, Act* out) -> int {
+        CKR(plan_act(pl, out, N, in.H / 2, in.W / 2, in.C));
+        Op op;
+        op.type = OP_MAXPOOL; op.name = "max_pool2d";
+        op.sp_in = in.base; op.sp_out = out->base; op.sp_N = N; op.sp_H = in.H; op.sp_W = in.W; op.sp_C = in.C;
+        pl->ops.push_back(op);
+        return W2L_OK;
+    };
+    Act a, b, taps[6];
+    CKR(conv(0, x, &a)); CKR(conv(1, a, &b)); CKR(pool(b, &a));
+    CKR(conv(2, a, &b)); CKR(conv(3, b, &a)); CKR(pool(a, &b));
+    CKR(conv(4, b, &a)); CKR(conv(5, a, &b)); CKR(conv(6, b, &taps[0])); CKR(pool(taps[0], &a));
+    CKR(conv(7, a, &b)); CKR(conv(8, b, &a)); CKR(conv(9, a, &taps[1])); CKR(pool(taps[1], &a));
+    CKR(conv(10, a, &b)); CKR(conv(11, b, &a)); CKR(conv(12, a, &taps[2])); CKR(pool(taps[2], &a));
+    CKR(conv(13, a, &b)); CKR(conv(14, b, &taps[3]));
+    CKR(conv(15, taps[3], &a)); CKR(conv(16, a, &taps[4]));
+    CKR(conv(17, taps[4], &a)); CKR(conv(18, a, &taps[5]));
+    for (int i = 0; i < 6; ++i) {
+        Act f = taps[i];
+        if (i < 3) {   // L2Norm(scale 10 / 8 / 5), net_s3fd.py:108-110
+            CKR(plan_act(pl, &f, N, taps[i].H, taps[i].W, taps[i].C));
+            Op op;
+            op.type = OP_CHAN_L2NORM; op.name = "L2Norm";
+            op.sp_in = taps[i].base; op.sp_out = f.base; op.sp_w = ctx->s3fd_l2w[i];
+            op.sp_N = N; op.sp_H = f.H; op.sp_W = f.W; op.sp_C = f.C;
+            pl->ops.push_back(op);
+        }
+        for (int h = 0; h < 2; ++h) {
+            const int li = 19 + 2 * i + h;
+            Act o;
+            CKR(conv(li, f, &o, true));
+            Op op;
+            op.type = OP_S3FD_EXPORT; op.name = sp.layers[li].name + ".export";
+            op.sp_f32 = (const float*)o.base; op.sp_N = N; op.sp_H = o.H; op.sp_W = o.W;
+            op.sp_Cout = h == 0 ? 2 : 4; op.sp_maxout = (i == 0 && h == 0) ? 1 : 0;
+            op.aux_out = 2 * i + h;
+            pl->ops.push_back(op);
+        }
+    }
+    return W2L_OK;
+}
+
+static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out, int H = 0, int W = 0) {
+    char key[96];
+    snprintf(key, sizeof(key), "%d:%d:%d:%d:%d:%d", net, B, T, (int)ctx->keep_all, H, W);
     auto it = ctx->plans.find(key);
     if (it != ctx->plans.end()) { it->second->last_used = ++ctx->plan_clock; *out = it->second.get(); return W2L_OK; }
     if (!ctx->nets[net].loaded) return fail(W2L_ESTATE, "weights of net %d not loaded", net);
@@ -230,12 +303,13 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
         ctx->plans.erase(lru);
     }
     std::unique_ptr<Plan> pl(new Plan());
-    pl->net = net; pl->B = B; pl->T = T;
+    pl->net = net; pl->B = B; pl->T = T; pl->H = H; pl->W = W;
     pl->x2 = ctx->x2;
     pl->N = (net == W2L_NET_SYNCNET) ? B : (T > 0 ? B * T : B);
     int r = W2L_OK;
     if (net == W2L_NET_GENERATOR) r = build_generator_plan(ctx, pl.get());
     else if (net == W2L_NET_SYNCNET) r = build_syncnet_plan(ctx, pl.get());
+    else if (net == W2L_NET_S3FD) r = build_s3fd_plan(ctx, pl.get());
     else r = build_disc_plan(ctx, pl.get());
     if (r != W2L_OK) { free_plan(pl.get()); return r; }
     pl->last_used = ++ctx->plan_clock;
@@ -245,7 +319,7 @@ static int get_plan(w2l_ctx* ctx, int net, int B, int T, Plan** out) {
 }
 
 static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, void* out0, void* out1, cudaStream_t st,
-                    bool u8 = false) {
+                    bool u8 = false, float* const* outs = nullptr) {
     const bool side = pl->has_side && ctx->use_side;
     cudaStream_t main_st = st;
     if (side) {
@@ -299,6 +373,29 @@ static int run_plan(w2l_ctx* ctx, Plan* pl, const void* in0, const void* in1, vo
             case OP_L2NORM: {
                 float* o = (float*)(op.aux_out == 0 ? out0 : out1);
                 l2norm_kernel<<<(op.aux_rows + 3) / 4, 128, 0, st>>>((const float*)op.aux_in, o, op.aux_rows, op.aux_dim);
+                ctx->launches++;
+                break;
+            }
+            case OP_MAXPOOL: {
+                const long long total = (long long)op.sp_N * (op.sp_H / 2) * (op.sp_W / 2) * (op.sp_C / 8);
+                const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+                if (ctx->bf16) maxpool2_kernel<true><<<blocks, 256, 0, st>>>(op.sp_in, op.sp_out, op.sp_N, op.sp_H, op.sp_W, op.sp_C);
+                else maxpool2_kernel<false><<<blocks, 256, 0, st>>>(op.sp_in, op.sp_out, op.sp_N, op.sp_H, op.sp_W, op.sp_C);
+                ctx->launches++;
+                break;
+            }
+            case OP_CHAN_L2NORM: {
+                const long long pixels = (long long)op.sp_N * op.sp_H * op.sp_W;
+                if (ctx->bf16) chan_l2norm_kernel<true><<<(unsigned)((pixels + 7) / 8), 256, 0, st>>>(op.sp_in, op.sp_out, op.sp_w, pixels, op.sp_C);
+                else chan_l2norm_kernel<false><<<(unsigned)((pixels + 7) / 8), 256, 0, st>>>(op.sp_in, op.sp_out, op.sp_w, pixels, op.sp_C);
+                ctx->launches++;
+                break;
+            }
+            case OP_S3FD_EXPORT: {
+                if (!outs) return fail(W2L_EINVAL, "S3FD plan needs its 12 output pointers");
+                const long long total = (long long)op.sp_N * op.sp_Cout * op.sp_H * op.sp_W;
+                const int blocks = (int)std::min<long long>((total + 255) / 256, ctx->num_sms * 16);
+                s3fd_export_kernel<<<blocks, 256, 0, st>>>(op.sp_f32, outs[op.aux_out], op.sp_N, op.sp_H, op.sp_W, op.sp_Cout, op.sp_maxout);
                 ctx->launches++;
                 break;
             }

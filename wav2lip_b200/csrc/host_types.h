@@ -36,11 +36,13 @@ static int fail(int code, const char* fmt, ...) {
 static const GeneratorSpec& gen_spec() { static GeneratorSpec s = build_generator_spec(); return s; }
 static const SyncnetSpec& sync_spec() { static SyncnetSpec s = build_syncnet_spec(); return s; }
 static const DiscSpec& disc_spec() { static DiscSpec s = build_disc_spec(); return s; }
+static const S3fdSpec& s3fd_spec() { static S3fdSpec s = build_s3fd_spec(); return s; }
 static const std::vector<Layer>* net_layers(int net) {
     switch (net) {
         case W2L_NET_GENERATOR: return &gen_spec().layers;
         case W2L_NET_SYNCNET: return &sync_spec().layers;
         case W2L_NET_DISC: return &disc_spec().layers;
+        case W2L_NET_S3FD: return &s3fd_spec().layers;
     }
     return nullptr;
 }
@@ -113,7 +115,7 @@ struct NetW {
     bool loaded = false;
 };
 
-enum OpType { OP_CONV = 0, OP_INGEST = 1, OP_L2NORM = 2, OP_DISC_HEAD = 3 };
+enum OpType { OP_CONV = 0, OP_INGEST = 1, OP_L2NORM = 2, OP_DISC_HEAD = 3, OP_MAXPOOL = 4, OP_CHAN_L2NORM = 5, OP_S3FD_EXPORT = 6 };
 
 struct Op {
     int type = OP_CONV;
@@ -140,12 +142,16 @@ struct Op {
     int aux_rows = 0, aux_dim = 0;
     int aux_out = 0;  // which caller output
     int aux_pitch = 0, aux_lo = 0;
+    // S3FD: max-pool / channel L2Norm / head export
+    const uint16_t* sp_in = nullptr; uint16_t* sp_out = nullptr; const float* sp_f32 = nullptr; const float* sp_w = nullptr;
+    int sp_N = 0, sp_H = 0, sp_W = 0, sp_C = 0, sp_Cout = 0, sp_maxout = 0;
     int lane = 0;          // 1: runs on the context's side stream (the audio encoder, concurrently with the face encoder)
     bool join_side = false;  // wait for the side stream before this op
 };
 
 struct Plan {
     int net = 0, B = 0, T = 0, N = 0;
+    int H = 0, W = 0;              // S3FD: image size
     std::vector<Op> ops;
     std::vector<void*> allocs;
     size_t bytes = 0;
@@ -178,9 +184,10 @@ struct w2l_ctx {
     bool use_pdl = true;      // W2L_DISABLE_PDL=1
     bool use_rowstack = true;  // W2L_DISABLE_ROWSTACK=1
     bool use_mel_v2 = true;    // W2L_DISABLE_MELV2=1
-    NetW nets[3];
+    NetW nets[4];
+    float* s3fd_l2w[3] = {nullptr, nullptr, nullptr};   // conv3_3_norm / conv4_3_norm / conv5_3_norm weights (fp32 copies)
     std::map<std::string, std::unique_ptr<Plan>> plans;
-    Plan* last_plan[3] = {nullptr, nullptr, nullptr};
+    Plan* last_plan[4] = {nullptr, nullptr, nullptr, nullptr};
     int64_t launches = 0;
     long long plan_clock = 0;
     size_t weight_bytes = 0;

@@ -102,7 +102,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
         PackedW pw;
         for (int r = 0; r < L.kh; ++r)
             for (int s = 0; s < L.kw; ++s) { rs.push_back({r, s}); pw.dy.push_back((signed char)(r - L.ph)); pw.dx.push_back((signed char)(s - L.pw)); }
-        CKR(pack_taps(ctx, &pw, W, L.cout, L.cin, L.kh, L.kw, false, rs, pad_to, st));
+        CKR(pack_taps(ctx, &pw, W, L.cout_real > 0 ? L.cout_real : L.cout, L.cin, L.kh, L.kw, false, rs, pad_to, st));
         lw->ph.push_back(pw);
     } else if (in_hw1 && !ctx->x2 && L.sh == 1 && L.sw == 1 && L.ph == 0 && L.pw == 0) {
         // out[n, y, x, co] = sum_ci in[n, ci] * W[ci, co, y, x]  -> GEMM with columns (y, x, co)
@@ -164,7 +164,7 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
     CKR(dev_alloc(&sc, (size_t)n_pad * 4));
     CKR(dev_alloc(&sh, (size_t)n_pad * 4));
     lw->scale = (float*)sc; lw->shift = (float*)sh; lw->n_scale = n_pad;
-    fold_bn_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, 1e-5f, L.cout, reps, n_pad, lw->scale, lw->shift);
+    fold_bn_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(bias, gamma, beta, mean, var, 1e-5f, L.cout_real > 0 ? L.cout_real : L.cout, reps, n_pad, lw->scale, lw->shift);
     if (ctx->fold_rec && bias) ctx->fold_rec->push_back(FoldJob{bias, L.cout, reps, n_pad, lw->scale, lw->shift});
     ctx->launches++;
     CK(cudaGetLastError());
@@ -174,9 +174,10 @@ static int load_layer(w2l_ctx* ctx, LayerW* lw, const Layer& L, const float* W, 
 
 static int fetch_block_tensors(const TensorMap& tm, const Layer& L, const float** W, const float** b, const float** g,
                                const float** be, const float** m, const float** v) {
-    const int64_t wn = (int64_t)L.cin * L.cout * L.kh * L.kw;
-    CKR(need(tm, L.name + ".conv_block.0.weight", wn, W));
-    CKR(need(tm, L.name + ".conv_block.0.bias", L.cout, b));
+    const int cout = L.cout_real > 0 ? L.cout_real : L.cout;
+    const int64_t wn = (int64_t)L.cin * cout * L.kh * L.kw;
+    CKR(need(tm, L.name + (L.bare_keys ? ".weight" : ".conv_block.0.weight"), wn, W));
+    CKR(need(tm, L.name + (L.bare_keys ? ".bias" : ".conv_block.0.bias"), cout, b));
     *g = *be = *m = *v = nullptr;
     if (L.kind == W2L_BLOCK_CONV_BN_RELU || L.kind == W2L_BLOCK_CONVT_BN_RELU) {
         CKR(need(tm, L.name + ".conv_block.1.weight", L.cout, g));

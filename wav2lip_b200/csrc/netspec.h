@@ -21,6 +21,8 @@ struct Layer {
     int kind;
     int cin, cout, kh, kw, sh, sw, ph, pw, out_pad;
     bool residual;
+    bool bare_keys = false;   // parameters are "<name>.weight" / "<name>.bias" (plain nn.Conv2d members: S3FD) instead of "<name>.conv_block.0.*"
+    int cout_real = 0;        // > 0: the tensor has this many output channels, `cout` is its 16-padded width (S3FD heads: 2 / 4)
 };
 
 inline Layer mk(const std::string& name, int kind, int cin, int cout, int k, int sh, int sw, int p, int op = 0,
@@ -167,6 +169,39 @@ inline DiscSpec build_disc_spec() {
     L.push_back(mk(pre + "6.0", NN, 512, 512, 3, 1, 1, 0));
     L.push_back(mk(pre + "6.1", NN, 512, 512, 1, 1, 1, 0));
     return d;
+}
+
+// face_detection/detection/sfd/net_s3fd.py:22-129.  Backbone layers 0..18 (conv + ReLU), heads 19..30 (conv only, output
+// channels padded to 16).  Pools, L2Norm and the taps are wired by the planner (host_plans.cuh: build_s3fd_plan).
+struct S3fdSpec {
+    std::vector<Layer> layers;
+};
+
+inline S3fdSpec build_s3fd_spec() {
+    S3fdSpec s;
+    auto& L = s.layers;
+    const int R = W2L_BLOCK_CONV_RELU, P = W2L_BLOCK_CONV_PLAIN;
+    auto add = [&](const char* name, int kind, int cin, int cout, int k, int stride, int pad, int cout_real = 0) {
+        Layer l = mk(name, kind, cin, cout, k, stride, stride, pad);
+        l.bare_keys = true;
+        l.cout_real = cout_real;
+        L.push_back(l);
+    };
+    add("conv1_1", R, 3, 64, 3, 1, 1);    add("conv1_2", R, 64, 64, 3, 1, 1);
+    add("conv2_1", R, 64, 128, 3, 1, 1);  add("conv2_2", R, 128, 128, 3, 1, 1);
+    add("conv3_1", R, 128, 256, 3, 1, 1); add("conv3_2", R, 256, 256, 3, 1, 1); add("conv3_3", R, 256, 256, 3, 1, 1);
+    add("conv4_1", R, 256, 512, 3, 1, 1); add("conv4_2", R, 512, 512, 3, 1, 1); add("conv4_3", R, 512, 512, 3, 1, 1);
+    add("conv5_1", R, 512, 512, 3, 1, 1); add("conv5_2", R, 512, 512, 3, 1, 1); add("conv5_3", R, 512, 512, 3, 1, 1);
+    add("fc6", R, 512, 1024, 3, 1, 3);    add("fc7", R, 1024, 1024, 1, 1, 0);
+    add("conv6_1", R, 1024, 256, 1, 1, 0); add("conv6_2", R, 256, 512, 3, 2, 1);
+    add("conv7_1", R, 512, 128, 1, 1, 0);  add("conv7_2", R, 128, 256, 3, 2, 1);
+    const char* taps[6] = {"conv3_3_norm", "conv4_3_norm", "conv5_3_norm", "fc7", "conv6_2", "conv7_2"};
+    const int tap_c[6] = {256, 512, 512, 1024, 512, 256};
+    for (int i = 0; i < 6; ++i) {
+        add((std::string(taps[i]) + "_mbox_conf").c_str(), P, tap_c[i], 16, 3, 1, 1, i == 0 ? 4 : 2);
+        add((std::string(taps[i]) + "_mbox_loc").c_str(), P, tap_c[i], 16, 3, 1, 1, 4);
+    }
+    return s;
 }
 
 }  // namespace w2l

@@ -60,6 +60,7 @@ int w2l_net_layer_info(int net, int index, w2l_layer_info* out) {
     snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
     out->kind = L.kind; out->cin = L.cin; out->cout = L.cout; out->kh = L.kh; out->kw = L.kw;
     out->sh = L.sh; out->sw = L.sw; out->ph = L.ph; out->pw = L.pw; out->out_pad = L.out_pad; out->residual = L.residual ? 1 : 0;
+    out->cout_real = L.cout_real;
     return W2L_OK;
 }
 
@@ -139,7 +140,8 @@ int w2l_destroy(w2l_ctx* ctx) {
     cudaDeviceSynchronize();
     free_train_state(ctx);
     for (auto& kv : ctx->plans) free_plan(kv.second.get());
-    for (int n = 0; n < 3; ++n) {
+    for (int i = 0; i < 3; ++i) if (ctx->s3fd_l2w[i]) cudaFree(ctx->s3fd_l2w[i]);
+    for (int n = 0; n < 4; ++n) {
         for (auto& lw : ctx->nets[n].layers) free_layer(lw);
         if (ctx->nets[n].head_w) cudaFree(ctx->nets[n].head_w);
         if (ctx->nets[n].head_b) cudaFree(ctx->nets[n].head_b);
@@ -196,7 +198,8 @@ int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* na
         CKR(fetch_block_tensors(tm, L, &W, &b, &gm, &be, &m, &v));
         const bool hw1 = (net == W2L_NET_GENERATOR && L.name == "face_decoder_blocks.1.0");
         // blocks fed directly by the ingest kernel (caller tensors): the only ones with a tiny Cin
-        bool first = L.name == "face_encoder_blocks.0.0" || L.name == "audio_encoder.0" || L.name == "face_encoder.0";
+        bool first = L.name == "face_encoder_blocks.0.0" || L.name == "audio_encoder.0" || L.name == "face_encoder.0" ||
+                     (net == W2L_NET_S3FD && L.name == "conv1_1");
         // the generator's 16->32 stride-2 block reads a dense zero-bordered copy of the first block's output (written by
         // the patch kernel's second TMA store) through the same overlapping-window trick
         if (net == W2L_NET_GENERATOR && L.name == "face_encoder_blocks.1.0" && ctx->use_patch && ctx->use_fold && ctx->use_fold_s2) first = true;
@@ -216,6 +219,16 @@ int w2l_load_weights(w2l_ctx* ctx, int net, int n_tensors, const char* const* na
         CKR(dev_alloc(&p, bcount * 4)); nw.head_b = (float*)p;
         CK(cudaMemcpyAsync(nw.head_w, hw, wcount * 4, cudaMemcpyDeviceToDevice, st));
         CK(cudaMemcpyAsync(nw.head_b, hb, bcount * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (net == W2L_NET_S3FD) {   // L2Norm weights (net_s3fd.py:12-14, :64-66)
+        const char* names3[3] = {"conv3_3_norm.weight", "conv4_3_norm.weight", "conv5_3_norm.weight"};
+        const int64_t n3[3] = {256, 512, 512};
+        for (int i = 0; i < 3; ++i) {
+            const float* w;
+            CKR(need(tm, names3[i], n3[i], &w));
+            if (!ctx->s3fd_l2w[i]) { void* p; CKR(dev_alloc(&p, 512 * 4)); ctx->s3fd_l2w[i] = (float*)p; }
+            CK(cudaMemcpyAsync(ctx->s3fd_l2w[i], w, n3[i] * 4, cudaMemcpyDeviceToDevice, st));
+        }
     }
     CK(cudaStreamSynchronize(st));  // the caller may free / mutate the fp32 sources after we return
     nw.loaded = true;
@@ -413,6 +426,26 @@ int w2l_lipsync_frames_u8(w2l_ctx* ctx, const float* mel, const uint8_t* frames,
     return W2L_OK;
 }
 
+
+// ---- scope row f4: S3FD network (face_detection/detection/sfd/net_s3fd.py:22-129) ----
+int w2l_s3fd_out_dims(int H, int W, int32_t* dims12) {
+    if (!dims12 || H < 32 || W < 32) return fail(W2L_EINVAL, "S3FD needs an image of at least 32 x 32");
+    int hs[6], ws[6];
+    s3fd_dims(H, W, hs, ws);
+    for (int i = 0; i < 6; ++i) { dims12[2 * i] = hs[i]; dims12[2 * i + 1] = ws[i]; }
+    return W2L_OK;
+}
+
+int w2l_s3fd_forward(w2l_ctx* ctx, const float* img, float* const* outs, int B, int H, int W, void* stream) {
+    if (!ctx || !img || !outs) return fail(W2L_EINVAL, "null argument");
+    for (int i = 0; i < 12; ++i) if (!outs[i]) return fail(W2L_EINVAL, "null output %d", i);
+    if (B <= 0 || H < 32 || W < 32) return fail(W2L_EINVAL, "bad shape B=%d H=%d W=%d", B, H, W);
+    DeviceGuard g(ctx->device);
+    Plan* pl;
+    CKR(get_plan(ctx, W2L_NET_S3FD, B, 0, &pl, H, W));
+    return run_plan(ctx, pl, img, nullptr, nullptr, nullptr, (cudaStream_t)stream, false, outs);
+}
+
 int w2l_syncnet_forward(w2l_ctx* ctx, const float* mel, const float* face, float* a_emb, float* v_emb, int B, void* stream) {
     if (!ctx || !mel || !face || !a_emb || !v_emb) return fail(W2L_EINVAL, "null argument");
     if (B <= 0) return fail(W2L_EINVAL, "bad batch %d", B);
@@ -535,7 +568,7 @@ int w2l_conv_block_forward(w2l_ctx* ctx, const w2l_layer_info* spec, const float
 }
 
 int w2l_debug_layer_output(w2l_ctx* ctx, int net, int layer, float* y, int* n, int* c, int* h, int* w, void* stream) {
-    if (!ctx || net < 0 || net > 2) return fail(W2L_EINVAL, "bad argument");
+    if (!ctx || net < 0 || net > 3) return fail(W2L_EINVAL, "bad argument");
     Plan* pl = ctx->last_plan[net];
     if (!pl) return fail(W2L_ESTATE, "no forward has run for net %d", net);
     auto it = pl->layer_out.find(layer);
@@ -967,7 +1000,7 @@ int64_t w2l_device_bytes(const w2l_ctx* ctx) {
 }
 
 int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out, char (*names_out)[64], void* stream) {
-    if (!ctx || net < 0 || net > 2 || iters <= 0) return fail(W2L_EINVAL, "bad argument");
+    if (!ctx || net < 0 || net > 3 || iters <= 0) return fail(W2L_EINVAL, "bad argument");
     Plan* pl = ctx->last_plan[net];
     if (!pl) return fail(W2L_ESTATE, "no forward has run for net %d", net);
     DeviceGuard g(ctx->device);
