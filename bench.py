@@ -169,6 +169,33 @@ def measure_extra(dev):
         out["disc"] = {"config": "Wav2Lip_disc_qual.forward B=256, T=5 (1280 frames, fp16 operands)", "ms": ms,
                        "frames_per_s": 1280 / ms * 1e3, "tflops": 1280 / ms * 1e3 * 2 * 1255850496 / 1e12}
         del d, frames
+        # scope row f4: the S3FD network on one face_det_batch (inference.py:43: 16 frames) of 720p frames
+        try:
+            from wav2lip_b200 import _lib as _L
+            from wav2lip_b200.face_detection.detection.sfd.net_s3fd import s3fd
+            fd = s3fd().to(dev).eval()
+            img = (torch.rand((16, 3, 720, 1280)) * 255 - 117).to(dev)
+            ms = timeit(lambda: fd(img), 5)
+            fl = sum(f for _, _, f in fd._w2l_ctx.profile_plan(_L.NET_S3FD, iters=1))
+            out["s3fd"] = {"config": "s3fd.forward, 16 frames of 1280x720 (face_det_batch_size, fp16 operands)", "ms": ms,
+                           "frames_per_s": 16 / ms * 1e3, "tflops": fl / ms / 1e9}
+            del fd, img
+        except Exception as e:
+            out["s3fd"] = {"error": repr(e)[:200]}
+        # frames in, frames out: the whole inner loop of inference.py in one call (crop, resize, generator, resize, paste)
+        try:
+            from wav2lip_b200.models import Wav2Lip as _G
+            gg = _G().to(dev).eval()
+            fr = torch.randint(0, 256, (32, 720, 1280, 3), dtype=torch.uint8, device=dev)
+            bx = [[i % 32, 200 + (i % 7), 520 + (i % 5), 500 + (i % 11), 800 + (i % 3)] for i in range(128)]
+            mm = (torch.rand((128, 1, 80, 16)) * 8 - 4).to(dev)
+            ms = timeit(lambda: gg.infer_frames(mm, fr, bx), 5)
+            out["infer_frames"] = {"config": "Wav2Lip.infer_frames: 128 mel chunks + 32 720p frames + boxes -> 128 finished 720p frames "
+                                             "(crop, cv2-exact resize, generator, resize, paste; 354 MB of frames written)", "ms": ms,
+                                   "frames_per_s": 128 / ms * 1e3}
+            del gg, fr
+        except Exception as e:
+            out["infer_frames"] = {"error": repr(e)[:200]}
         # fused uint8 batch assembly (scope row f): host uint8 crops + fp32 mels in, host uint8 predictions out
         import ctypes as C
         from wav2lip_b200 import _lib

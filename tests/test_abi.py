@@ -106,6 +106,10 @@ def test_drop_in_shadowing_of_reference_packages(lib):
     code = ("from models import Wav2Lip, Wav2Lip_disc_qual\n"
             "from models import SyncNet_color as SyncNet\n"
             "import audio\n"
+            "import face_detection\n"                                    # inference.py:4, :75-77
+            "from face_detection.detection.sfd.net_s3fd import s3fd\n"
+            "assert hasattr(audio, 'load_wav') and hasattr(face_detection, 'FaceAlignment') and face_detection.LandmarksType._2D\n"
+            "assert len(s3fd().state_dict()) == 65\n"
             "m = Wav2Lip()\n"
             "print(len(m.state_dict()), len(SyncNet().state_dict()), audio.num_frames(16000), audio.melspectrogram.__module__)\n")
     env = dict(os.environ, PYTHONPATH=os.path.join(ROOT, "wav2lip_b200"))
