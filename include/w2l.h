@@ -302,7 +302,8 @@ int64_t w2l_launch_count(const w2l_ctx* ctx);
 /* bytes of device memory currently held by the context (weights + activation arenas) */
 int64_t w2l_device_bytes(const w2l_ctx* ctx);
 /* Time the conv kernels of the last-built plan of `net` individually: runs every launch `iters`
- * times with CUDA events on `stream` and writes per-launch mean milliseconds and flop counts.
+ * times with CUDA events on `stream`, the L2 flushed before each timed launch (cold cache, as in the step), and writes
+ * per-launch mean milliseconds and flop counts.
  * Returns the number of launches written (<= cap). */
 int w2l_profile_plan(w2l_ctx* ctx, int net, int iters, int cap, float* ms_out, double* flop_out,
                      char (*names_out)[64], void* stream);

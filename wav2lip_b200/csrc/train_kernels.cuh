@@ -454,8 +454,11 @@ __global__ void gen_loss_grad_kernel(const GenLossGradParams p) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % 96), yy = (int)((i / 96) % 96);
         const int t = (int)((i / 9216) % p.T), c = (int)((i / (9216LL * p.T)) % 3), b = (int)(i / (9216LL * p.T * 3));
-        const float diff = p.g[i] - p.gt[i];
-        float d = diff > 0.0f ? p.l1_scale : (diff < 0.0f ? -p.l1_scale : 0.0f);
+        float d = 0.0f;
+        if (p.g) {   // (null in the stand-alone bridge: only an input gradient is scattered, w2l_train_backward)
+            const float diff = p.g[i] - p.gt[i];
+            d = diff > 0.0f ? p.l1_scale : (diff < 0.0f ? -p.l1_scale : 0.0f);
+        }
         if (yy >= 48) {
             if (p.dsync) d += from16<kBF16>(p.dsync[(((long long)b * 48 + (yy - 48)) * 96 + x) * 16 + 3 * t + c]);
             if (p.ddisc) d += from16<kBF16>(p.ddisc[((((long long)t * p.B + b) * 48 + (yy - 48)) * 96 + x) * 16 + c]);
