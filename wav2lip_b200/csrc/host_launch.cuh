@@ -137,6 +137,14 @@ static int launch_conv(w2l_ctx* ctx, const Op& op, cudaStream_t st, bool pdl = t
         ctx->launches++;
         return W2L_OK;
     }
+    if (op.swap) {
+        static uint64_t attr_set[2] = {0, 0};
+        void (*fn)(const ConvParams) = ctx->bf16 ? conv_swap_kernel<true> : conv_swap_kernel<false>;
+        CKR(ensure_smem_attr(&attr_set[ctx->bf16 ? 1 : 0], ctx->device, (const void*)fn, SwapCfg::kSmemBytes));
+        CK(launch_k(fn, op.grid, SwapCfg::kThreads, (size_t)SwapCfg::kSmemBytes, st, op.cp, pdl));
+        ctx->launches++;
+        return W2L_OK;
+    }
     ConvKernelEntry* e = find_conv_kernel(op.BN, op.BK, ctx->bf16, op.head, op.MT);
     if (!e) return fail(W2L_EINVAL, "no conv kernel for BN=%d BK=%d head=%d MT=%d", op.BN, op.BK, (int)op.head, op.MT);
     CKR(ensure_smem_attr(&e->attr_set, ctx->device, (const void*)e->fn, e->smem));

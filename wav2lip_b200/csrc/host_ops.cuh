@@ -332,7 +332,10 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     if (ctx->use_mt2 && !a.head && find_conv_kernel(BN, BK, ctx->bf16, false, 2) &&
         (long long)((m_tiles + 1) / 2) * n_tiles_ >= 2LL * ctx->num_sms)
         op.MT = 2;
-    if (op.MT == 2) op.name += " [2M]";
+    // 128-channel tiles with two pixel tiles per unit: one M=128(channels) x N=256(pixels) instruction per K step instead of
+    // two N=128 ones (conv_swap.cuh: 96 instead of 128 B/clk of shared-memory operand reads)
+    if (ctx->use_swap && ctx->use_tma_epi && op.MT == 2 && BN == 128 && BK == 64 && !ctx->x2 && !a.out.f32) op.swap = true;
+    if (op.MT == 2) op.name += op.swap ? " [swap]" : " [2M]";
 
     ConvParams& p = op.cp;
     memset(&p, 0, sizeof(p));

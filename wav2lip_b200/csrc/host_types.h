@@ -127,6 +127,7 @@ struct Op {
     int grid = 0;
     double flops = 0;  // algorithmic (true MACs*2), not padded
     bool patch = false;  // conv_patch_kernel instead of conv_igemm_kernel
+    bool swap = false;   // conv_swap_kernel (M = channels, N = 256 pixels) instead of conv_igemm_kernel<128,64,.,.,2>
     PatchParams pp;
     int dyn_smem = 0;
     bool ctf = false;   // convt_fused_kernel
@@ -177,6 +178,7 @@ struct w2l_ctx {
     bool use_patch = true;   // W2L_DISABLE_HALO=1 turns the patch kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
     bool use_mt2 = true;    // W2L_DISABLE_MT2=1
+    bool use_swap = true;   // W2L_DISABLE_SWAP=1: conv_swap_kernel (channel-major accumulator) for the 128-channel-tile layers
     bool use_tma_epi = true;  // W2L_DISABLE_TMAEPI=1
     bool use_fold_s2 = true;  // W2L_DISABLE_FOLDS2=1
     bool use_ctfused = true;  // W2L_DISABLE_CTFUSED=1

@@ -21,6 +21,7 @@
 #include "aux_kernels.cuh"
 #include "conv_patch.cuh"
 #include "conv_rowstack.cuh"
+#include "conv_swap.cuh"
 #include "conv_tcgen05.cuh"
 #include "convt_fused.cuh"
 #include "mel.cuh"
@@ -112,6 +113,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_fold_s2 = enabled("W2L_DISABLE_FOLDS2");
         ctx->use_bn256 = enabled("W2L_DISABLE_BN256");
         ctx->use_mt2 = enabled("W2L_DISABLE_MT2");
+        ctx->use_swap = enabled("W2L_DISABLE_SWAP");
         ctx->use_tma_epi = enabled("W2L_DISABLE_TMAEPI");
         ctx->use_ctfused = enabled("W2L_DISABLE_CTFUSED");
         ctx->use_rowstack = enabled("W2L_DISABLE_ROWSTACK");
