@@ -33,6 +33,8 @@ struct TBlock {
     float* y_f32 = nullptr;      // optional fp32 copy of y (embeddings)
     bool bn = true;
     bool wgrad_only = false;     // backward of this block only serves parameter gradients (the expert's audio branch)
+    Act x_fold;                  // first blocks: the K-folded copy of the input the forward reads (base == nullptr: none)
+    int fold_cp = 0;             // ... and its channel pitch: window element s*fold_cp + c = horizontal tap s, channel c
     float *stats = nullptr, *coef = nullptr, *partial = nullptr;
     int nblk = 0;
     long long M = 0;             // output pixels N*Ho*Wo
@@ -230,9 +232,14 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     // when the input is wide and the output narrow (the 80 -> 32 output block) put x on the M side and dz, with all its taps
     // in one group, on the N side — one pass over the pixels instead of three
     const bool swap = !convT && L.sh == 1 && L.sw == 1 && L.cin > 64 && L.cout <= 64;
+    // K-folded first layers (7x7 on 6 / 3 channels): the shifted operand is the forward's folded copy of the input, whose
+    // 64-element window at pixel x holds the kw horizontal taps side by side — kh loads of 128-byte rows per pixel chunk
+    // instead of kh*kw loads of 32-byte rows (the plain form was TMA-request-bound: 1.5 ms for 28 GFLOP)
+    const bool folded = !convT && !swap && b->x_fold.base != nullptr && b->x_fold.C == 64 && L.sh == 1 && L.sw == 1 &&
+                        L.kw * b->fold_cp <= 64;
     const Act& S = (convT || swap) ? b->x : b->dz;     // on the dense pixel grid of the sum
-    const Act& Tt = (convT || swap) ? b->dz : b->x;    // read shifted / strided
-    const int Cm = (convT || swap) ? L.cin : L.cout, Cn = (convT || swap) ? L.cout : L.cin;
+    const Act& Tt = folded ? b->x_fold : ((convT || swap) ? b->dz : b->x);    // read shifted / strided
+    const int Cm = (convT || swap) ? L.cin : L.cout, Cn = folded ? 64 : ((convT || swap) ? L.cout : L.cin);
     WgradOp& w = b->wg;
     w.on = true;
     const int cn_pad = Tt.C;                 // channels of the view (first layers: padded to 16)
@@ -240,17 +247,21 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     w.BN = BN;
     WgradParams& p = w.wp;
     memset(&p, 0, sizeof(p));
-    p.ntaps = L.kh * L.kw;
+    p.ntaps = folded ? L.kh : L.kh * L.kw;
     if (p.ntaps > kWgMaxTaps) return fail(W2L_EINVAL, "%s: too many taps for wgrad", L.name.c_str());
     const int max_tg = kWgTmemCols / BN;
     p.ngroups = (p.ntaps + max_tg - 1) / max_tg;
     p.tg = (p.ntaps + p.ngroups - 1) / p.ngroups;
     p.ngroups = (p.ntaps + p.tg - 1) / p.tg;
-    for (int r = 0; r < L.kh; ++r)
-        for (int s = 0; s < L.kw; ++s) {
-            p.dy[r * L.kw + s] = (signed char)(swap ? L.ph - r : r - L.ph);
-            p.dx[r * L.kw + s] = (signed char)(swap ? L.pw - s : s - L.pw);
-        }
+    if (folded) {
+        for (int r = 0; r < L.kh; ++r) { p.dy[r] = (signed char)(r - L.ph); p.dx[r] = 0; }   // the window already starts at the leftmost tap
+    } else {
+        for (int r = 0; r < L.kh; ++r)
+            for (int s = 0; s < L.kw; ++s) {
+                p.dy[r * L.kw + s] = (signed char)(swap ? L.ph - r : r - L.ph);
+                p.dx[r * L.kw + s] = (signed char)(swap ? L.pw - s : s - L.pw);
+            }
+    }
     p.sx = L.sw; p.sy = L.sh;
     // pixels per chunk: at least three pipeline stages must fit
     int maxP = (kWgSmemMax - 1024) / 3 / (256 + p.tg * BN * 2) / 16 * 16;
@@ -281,6 +292,7 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     WgradReduceParams& r = w.rp;
     r.ws = nullptr; r.out = b->gW; r.splits = p.splits; r.ntaps = p.ntaps; r.Cm = Cm; r.Cn = Cn; r.Mp = Mp; r.Np = Np; r.accumulate = 0;
     r.transpose = swap ? 1 : 0;
+    r.fold_kw = folded ? L.kw : 0; r.fold_cp = folded ? b->fold_cp : 0; r.fold_cin = folded ? L.cin : 0;
     w.flops = 2.0 * (double)L.cin * L.cout * L.kh * L.kw * (double)S.N * S.H * S.W;
     return W2L_OK;
 }
@@ -352,6 +364,7 @@ static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const L
         add_ingest(&tp->pl, "ingest.fold", fold->src_id, x_fwd, fold->B, fold->C, fold->sB, fold->sC, fold->sT, fold->y_off, fold->Wsrc);
         tp->pl.ops.back().ip.cgrp = fold->cgrp; tp->pl.ops.back().ip.sG = fold->sG;
         tp->ingest.push_back(tp->pl.ops.size() - 1);
+        b.x_fold = x_fwd; b.fold_cp = tp->wf.layers[li].ph[0].Cp;
     }
     b.fwd0 = tp->pl.ops.size();
     {

@@ -242,6 +242,9 @@ struct WgradReduceParams {
     long long Mp, Np;
     int accumulate;
     int transpose;   // 1: the parameter layout is [n][m][tap] (a conv whose operand roles were swapped: m = ci, n = co)
+    // K-folded first layers: a "tap" is a filter ROW r and column n = s*fold_cp + c is horizontal tap s, input channel c
+    // (fold_kw = 0: off); the parameter element is out[m][c][r][s]
+    int fold_kw, fold_cp, fold_cin;
 };
 
 // grid = (ceil(Cn / 64), Cm), block = 256: a block sums the splits of one row m, 64 columns n, all taps — reading the
@@ -272,6 +275,17 @@ __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const WgradReducePara
     }
     __syncthreads();
     const int ncols = min(64, p.Cn - n0);
+    if (p.fold_kw > 0) {
+        for (int i = threadIdx.x; i < ncols * p.ntaps; i += 256) {
+            const int n = i / p.ntaps, r = i - n * p.ntaps;
+            const int sx = (n0 + n) / p.fold_cp, c = (n0 + n) - sx * p.fold_cp;
+            if (sx >= p.fold_kw || c >= p.fold_cin) continue;
+            const float v = red_t[n * pitch + r];
+            float* o = p.out + (((long long)m * p.fold_cin + c) * p.ntaps + r) * p.fold_kw + sx;
+            *o = p.accumulate ? *o + v : v;
+        }
+        return;
+    }
     for (int i = threadIdx.x; i < ncols * p.ntaps; i += 256) {
         const int n = i / p.ntaps, t = i - n * p.ntaps;
         const float v = red_t[n * pitch + t];
