@@ -558,13 +558,14 @@ def main():
                     "whole_step_tflops": value / world * FLOP_PER_CROP / 1e12,
                     "traffic": None}
         # DRAM bytes of the same launches from the committed ncu capture (profiles/), valid for the default workload
-        tp = os.path.join(ROOT, "profiles", "r1_final_ncu_dram_per_step.json")
-        if os.path.exists(tp) and (B, T) == (B_DEFAULT, T_DEFAULT):
-            tj = json.load(open(tp))
+        tname = next((n for n in ("r2_final_ncu_dram_per_step.json", "r1_final_ncu_dram_per_step.json")
+                      if os.path.exists(os.path.join(ROOT, "profiles", n))), None)
+        if tname and (B, T) == (B_DEFAULT, T_DEFAULT):
+            tj = json.load(open(os.path.join(ROOT, "profiles", tname)))
             roofline["traffic"] = tj["dram_read_bytes"] + tj["dram_write_bytes"]
             roofline["traffic_note"] = ("dram__bytes_read+write summed over the %d conv launches of one step (ncu, profiles/"
-                                        "r1_final_ncu_dram_per_step.json); algorithmic conv in+out bytes per step = %.2f GB"
-                                        % (tj["launches"], (4.81e6 + 4.49e6) * 2 * N / 1e9))
+                                        "%s); algorithmic conv in+out bytes per step = %.2f GB"
+                                        % (tj["launches"], tname, (4.81e6 + 4.49e6) * 2 * N / 1e9))
         if args.profile_out and rank == 0:
             with open(args.profile_out, "w") as f:
                 f.write(f"# per-launch CUDA-event times, B={B} T={T} (N={N}), {len(prof)} conv launches, sum {conv_ms:.3f} ms\n")
