@@ -28,6 +28,14 @@ with torch.no_grad():
     cr = g.crop_resize(frames, boxes)
     pa = g.paste(u[:2], frames, boxes)
     fr = g.infer_frames(torch.rand(2, 1, 80, 16).cuda(), frames, boxes)
+    # conv_swap_kernel (needs >= 296 units of 256 pixels): a 128-channel residual block and a transposed-conv phase set
+    from wav2lip_b200.models.conv import Conv2d, Conv2dTranspose
+    sw = Conv2d(128, 128, 3, 1, 1, residual=True).cuda().eval()(torch.rand(140, 128, 24, 24).cuda())
+    swt = Conv2dTranspose(320, 128, 3, 2, 1, 1).cuda().eval()(torch.rand(150, 320, 12, 12).cuda())
+    # scope row f4: the S3FD detector network
+    from wav2lip_b200.face_detection.detection.sfd.net_s3fd import s3fd
+    det = s3fd().cuda().eval()
+    dm = det(torch.rand(1, 3, 96, 128).cuda() * 255)
     torch.cuda.synchronize()
 # scope row f1: one training iteration through the autograd bridge and one fused native step (B=1, T=5)
 from wav2lip_b200.training import Wav2LipTrainStep
