@@ -280,7 +280,8 @@ static int make_wgrad_op(w2l_ctx* ctx, TrainPlan* tp, TBlock* b, size_t* ws_need
     w.smem = p.stages * p.stage_bytes + 2048;
     // split K so that about two waves of units exist, each with enough chunks to amortise the pipeline fill
     const long long base_units = (long long)p.m_tiles * p.n_tiles * p.ngroups;
-    long long splits = (2LL * ctx->num_sms + base_units - 1) / base_units;
+    // (rounded DOWN: units are dealt round-robin to one persistent CTA per SM, so 2 * SMs + 1 units would cost three rounds)
+    long long splits = (2LL * ctx->num_sms) / base_units;
     splits = std::max(1LL, std::min(splits, std::max(1LL, p.chunks / 8)));
     splits = std::min(splits, 256LL);
     p.splits = (int)splits;
