@@ -15,7 +15,7 @@ from oracle import w2l_oracle as O
 pytestmark = pytest.mark.gpu
 
 FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED", "W2L_DISABLE_MT2", "W2L_DISABLE_TMAEPI", "W2L_DISABLE_FOLDS2", "W2L_DISABLE_ROWSTACK",
-         "W2L_DISABLE_SIDESTREAM"]
+         "W2L_DISABLE_SIDESTREAM", "W2L_DISABLE_SWAP"]
 
 
 def _fresh_generator(env):
@@ -64,6 +64,23 @@ def test_variants_agree_with_each_other():
     # each is within ~4e-3 of the fp32 reference on these stress weights (fp16 rounding points differ per tiling)
     assert (outs[0] - outs[1]).abs().max().item() <= 8e-3
     assert (outs[0] - outs[1]).abs().mean().item() <= 4e-4
+
+
+def test_swap_kernel_agrees_with_generic_kernel_at_inference_batch():
+    """conv_swap_kernel (csrc/conv_swap.cuh: M = channels, N = 256 pixels) is only chosen when a layer has >= 2 x 148 units,
+    i.e. at real batch sizes: N = 128 (inference.py's batch) with and without it.  Same operands, same K order, fp32
+    accumulation, one rounding per stored activation: the outputs are bit-identical."""
+    mel, face = O.make_generator_inputs(128, seed=9)
+    outs = []
+    for env in ({}, {"W2L_DISABLE_SWAP": "1"}):
+        g = _fresh_generator(env)
+        with torch.no_grad():
+            outs.append(g(mel.cuda(), face.cuda()).cpu())
+        names = [nm for nm, _ms, _fl in g._w2l_ctx.profile_plan(0, 1)]
+        assert any("[swap]" in n for n in names) == (not env), names
+    # measured: bit-identical (the instruction accumulates the same products in the same K order whichever operand is
+    # called A, and the epilogue arithmetic is the same fp32 fma / add / max / round)
+    assert torch.equal(outs[0], outs[1]), (outs[0] - outs[1]).abs().max().item()
 
 
 @pytest.mark.parametrize("B,T", [(5, 0), (70, 0), (3, 5), (67, 2)])
