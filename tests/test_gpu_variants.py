@@ -15,7 +15,7 @@ from oracle import w2l_oracle as O
 pytestmark = pytest.mark.gpu
 
 FLAGS = ["W2L_DISABLE_HALO", "W2L_DISABLE_FOLD", "W2L_DISABLE_BN256", "W2L_DISABLE_CTFUSED", "W2L_DISABLE_MT2", "W2L_DISABLE_TMAEPI", "W2L_DISABLE_FOLDS2", "W2L_DISABLE_ROWSTACK",
-         "W2L_DISABLE_SIDESTREAM", "W2L_DISABLE_SWAP"]
+         "W2L_DISABLE_SIDESTREAM", "W2L_DISABLE_SWAP", "W2L_DISABLE_ROUNDS"]
 
 
 def _fresh_generator(env):

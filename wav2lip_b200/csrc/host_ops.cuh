@@ -325,6 +325,19 @@ static int make_conv_op(w2l_ctx* ctx, Plan* pl, const ConvArgs& a) {
     if (a.head) BN = 32;
     else
         while (BN > 32 && m_tiles * (a.cout / BN) < ctx->num_sms && a.cout % (BN / 2) == 0) BN /= 2;
+    // Few-tile layers (<= 6x6 maps at 512 channels): units are dealt round-robin to one CTA per SM, so what counts is
+    // rounds x time per unit.  A K step of one unit costs ~137 cycles at N = 256, ~91 at N = 128, ~68 at N <= 64 (the
+    // operand-path model of DESIGN.md section 3): 90 units of 256 channels in ONE round beat 180 units of 128 in two.
+    // (only with a deep K loop, >= 36 steps: short ones are dominated by the 4-pass epilogue of the wide tile; measured
+    //  profiles/r2_rounds_ab_*: 512-channel 3x3 blocks at 3x3 57 -> 48 us, 4-tap phase 52 -> 44, 1- and 2-tap phases +2..3)
+    if (!a.head && ctx->use_bn256 && ctx->use_rounds && BK == 64 && BN < 256 && a.cout % 256 == 0 && w.cout_pad % 256 == 0 &&
+        w.ntaps * (w.cin_pad / BK) >= 36) {
+        auto rounds = [&](long long units) { return (units + ctx->num_sms - 1) / ctx->num_sms; };
+        const long long cost_cur = rounds((long long)m_tiles * (a.cout / BN)) * (BN == 128 ? 91 : 68);
+        const long long cost_256 = rounds((long long)m_tiles * (a.cout / 256)) * 137;
+        const bool mt2_ahead = ctx->use_mt2 && (long long)((m_tiles + 1) / 2) * (a.cout / BN) >= 2LL * ctx->num_sms;   // handled below
+        if (!mt2_ahead && cost_256 < cost_cur) BN = 256;
+    }
     if (w.cout_pad % BN != 0) return fail(W2L_EINVAL, "%s: cout_pad %d vs BN %d", a.name.c_str(), w.cout_pad, BN);
     op.BN = BN; op.BK = BK; op.head = a.head;
     // two M tiles per CTA (shared weight slab, two accumulators) once there is plenty of work

@@ -114,6 +114,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_bn256 = enabled("W2L_DISABLE_BN256");
         ctx->use_mt2 = enabled("W2L_DISABLE_MT2");
         ctx->use_swap = enabled("W2L_DISABLE_SWAP");
+        ctx->use_rounds = enabled("W2L_DISABLE_ROUNDS");
         ctx->use_tma_epi = enabled("W2L_DISABLE_TMAEPI");
         ctx->use_ctfused = enabled("W2L_DISABLE_CTFUSED");
         ctx->use_rowstack = enabled("W2L_DISABLE_ROWSTACK");
