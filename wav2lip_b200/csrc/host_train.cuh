@@ -95,6 +95,9 @@ struct TrainState {
     NcclAllReduceFn all_reduce = nullptr; NcclCommDestroyFn comm_destroy = nullptr; NcclGetErrorStringFn err_string = nullptr;
     cudaStream_t s_comm = nullptr; cudaEvent_t ev_bucket = nullptr, ev_comm = nullptr;
     double last_allreduce_bytes = 0;
+    // the weight-gradient GEMMs are leaves of the backward graph: they run on a side stream beside the dgrad chain, so that
+    // they fill the SMs the chain's partial rounds (and, at small batches, its latency-bound launches) leave idle
+    cudaStream_t s_wg = nullptr; cudaEvent_t ev_dz = nullptr, ev_wg = nullptr, ev_wgb = nullptr;
 };
 
 static TrainState* train_state(w2l_ctx* ctx) {
@@ -123,6 +126,8 @@ static void free_train_state(w2l_ctx* ctx) {
     if (ts->s_comm) cudaStreamDestroy(ts->s_comm);
     if (ts->ev_bucket) cudaEventDestroy(ts->ev_bucket);
     if (ts->ev_comm) cudaEventDestroy(ts->ev_comm);
+    if (ts->s_wg) cudaStreamDestroy(ts->s_wg);
+    for (cudaEvent_t e : {ts->ev_dz, ts->ev_wg, ts->ev_wgb}) if (e) cudaEventDestroy(e);
     delete ts;
     ctx->train = nullptr;
 }
@@ -682,7 +687,19 @@ static int block_forward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool update_run
     return W2L_OK;
 }
 
-static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bool accumulate, cudaStream_t st) {
+static int ensure_wg_stream(TrainState* ts) {
+    if (ts->s_wg) return W2L_OK;
+    CK(cudaStreamCreateWithFlags(&ts->s_wg, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ts->ev_dz, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ts->ev_wg, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ts->ev_wgb, cudaEventDisableTiming));
+    return W2L_OK;
+}
+
+// s_wg != nullptr: the block's wgrad (+ its split-K reduction) goes to that stream, ordered after this block's dz (ev);
+// the caller joins the stream before anything consumes the parameter gradients.
+static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bool accumulate, cudaStream_t st,
+                          cudaStream_t s_wg = nullptr, cudaEvent_t ev = nullptr) {
     const int C = b.L.cout;
     ChanReduceParams rp;
     memset(&rp, 0, sizeof(rp));
@@ -718,8 +735,14 @@ static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bo
             ctx->launches++;
         }
     }
+    const bool side = s_wg != nullptr && wgrad && b.wg.on;
+    if (side) {
+        CK(cudaEventRecord(ev, st));
+        CK(cudaStreamWaitEvent(s_wg, ev, 0));
+        CKR(launch_wgrad(ctx, tp, b, accumulate, s_wg));
+    }
     for (size_t i = b.dg0; i < b.dg1; ++i) CKR(launch_conv(ctx, tp->pl.ops[i], st));
-    if (wgrad && b.wg.on) CKR(launch_wgrad(ctx, tp, b, accumulate, st));
+    if (!side && wgrad && b.wg.on) CKR(launch_wgrad(ctx, tp, b, accumulate, st));
     return W2L_OK;
 }
 
@@ -806,12 +829,18 @@ static int train_backward(w2l_ctx* ctx, TrainPlan* tp, const float* d0, const fl
         else disc_head_bwd_kernel<false><<<1, 512, 0, st>>>(tp->feat.ptr(), tp->feat.Cs, hw, tp->prob_out, d0, tp->N, 512, tp->dfeat.ptr(), dw, db, accf);
         ctx->launches++;
     }
+    cudaStream_t s_wg = nullptr;
+    if (wgrad && ctx->use_wg_stream) { CKR(ensure_wg_stream(ts)); s_wg = ts->s_wg; }
     for (size_t k = tp->blocks.size(); k-- > 0;) {
         TBlock& b = tp->blocks[k];
         // a frozen expert inside the generator step only needs the face branch: skip blocks whose gradient goes nowhere
         if (!wgrad && b.wgrad_only) continue;
-        CKR(block_backward(ctx, tp, b, wgrad, acc, st));
+        CKR(block_backward(ctx, tp, b, wgrad, acc, st, s_wg, ts->ev_dz));
         if (after_block) CKR((*after_block)(k));
+    }
+    if (s_wg) {   // join: whatever follows on `st` (Adam, the caller's optimizer, the next forward) sees every gradient
+        CK(cudaEventRecord(ts->ev_wg, s_wg));
+        CK(cudaStreamWaitEvent(st, ts->ev_wg, 0));
     }
     CK(cudaGetLastError());
     return W2L_OK;
@@ -912,6 +941,10 @@ static int all_reduce_ranges(w2l_ctx* ctx, const std::vector<GradRange>& ranges,
     if (ts->world <= 1 || !ts->comm) return W2L_OK;
     CK(cudaEventRecord(ts->ev_bucket, compute));
     CK(cudaStreamWaitEvent(ts->s_comm, ts->ev_bucket, 0));
+    if (ts->s_wg) {   // the bucket's weight gradients were queued on the wgrad stream
+        CK(cudaEventRecord(ts->ev_wgb, ts->s_wg));
+        CK(cudaStreamWaitEvent(ts->s_comm, ts->ev_wgb, 0));
+    }
     for (const GradRange& r : ranges) {
         const int rc = ts->all_reduce(r.p, r.p, (size_t)r.n, /*ncclFloat32*/ 7, /*ncclAvg*/ 4, ts->comm, ts->s_comm);
         if (rc != 0) return fail(W2L_ECUDA, "ncclAllReduce failed: %s", ts->err_string ? ts->err_string(rc) : "?");
