@@ -24,6 +24,8 @@ struct WgradOp {
     double flops = 0;
 };
 
+static bool starts_with(const std::string& s, const char* prefix) { return s.rfind(prefix, 0) == 0; }
+
 struct TBlock {
     int li = 0;
     Layer L, Ld;                 // the block, and its input-gradient computation written as a block of the same table
@@ -33,6 +35,7 @@ struct TBlock {
     float* y_f32 = nullptr;      // optional fp32 copy of y (embeddings)
     bool bn = true;
     bool wgrad_only = false;     // backward of this block only serves parameter gradients (the expert's audio branch)
+    int lane = 0;                // 1: audio-encoder block — independent of the face encoder, runs on the auxiliary stream beside it
     Act x_fold;                  // first blocks: the K-folded copy of the input the forward reads (base == nullptr: none)
     int fold_cp = 0;             // ... and its channel pitch: window element s*fold_cp + c = horizontal tap s, channel c
     float *stats = nullptr, *coef = nullptr, *partial = nullptr;
@@ -98,6 +101,8 @@ struct TrainState {
     // the weight-gradient GEMMs are leaves of the backward graph: they run on a side stream beside the dgrad chain, so that
     // they fill the SMs the chain's partial rounds (and, at small batches, its latency-bound launches) leave idle
     cudaStream_t s_wg = nullptr; cudaEvent_t ev_dz = nullptr, ev_wg = nullptr, ev_wgb = nullptr;
+    // the audio encoder (small, latency-bound launches) runs beside the face encoder, forward and backward
+    cudaStream_t s_aux = nullptr; cudaEvent_t ev_aux_fork = nullptr, ev_aux_join = nullptr;
 };
 
 static TrainState* train_state(w2l_ctx* ctx) {
@@ -127,7 +132,8 @@ static void free_train_state(w2l_ctx* ctx) {
     if (ts->ev_bucket) cudaEventDestroy(ts->ev_bucket);
     if (ts->ev_comm) cudaEventDestroy(ts->ev_comm);
     if (ts->s_wg) cudaStreamDestroy(ts->s_wg);
-    for (cudaEvent_t e : {ts->ev_dz, ts->ev_wg, ts->ev_wgb}) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {ts->ev_dz, ts->ev_wg, ts->ev_wgb, ts->ev_aux_fork, ts->ev_aux_join}) if (e) cudaEventDestroy(e);
+    if (ts->s_aux) cudaStreamDestroy(ts->s_aux);
     delete ts;
     ctx->train = nullptr;
 }
@@ -405,6 +411,7 @@ static int add_train_block(w2l_ctx* ctx, TrainPlan* tp, int net, int li, const L
         b.dg1 = tp->pl.ops.size();
     }
     if (want_wgrad) CKR(make_wgrad_op(ctx, tp, &b, ws_need));
+    b.lane = starts_with(L.name, "audio_encoder.") ? 1 : 0;
     tp->blocks.push_back(b);
     return W2L_OK;
 }
@@ -696,6 +703,18 @@ static int ensure_wg_stream(TrainState* ts) {
     return W2L_OK;
 }
 
+static int ensure_aux_stream(TrainState* ts) {
+    if (ts->s_aux) return W2L_OK;
+    CK(cudaStreamCreateWithFlags(&ts->s_aux, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&ts->ev_aux_fork, cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&ts->ev_aux_join, cudaEventDisableTiming));
+    return W2L_OK;
+}
+static bool has_aux_lane(const TrainPlan* tp) {
+    for (const TBlock& b : tp->blocks) if (b.lane == 1) return true;
+    return false;
+}
+
 // s_wg != nullptr: the block's wgrad (+ its split-K reduction) goes to that stream, ordered after this block's dz (ev);
 // the caller joins the stream before anything consumes the parameter gradients.
 static int block_backward(w2l_ctx* ctx, TrainPlan* tp, TBlock& b, bool wgrad, bool accumulate, cudaStream_t st,
@@ -754,7 +773,27 @@ static int train_forward(w2l_ctx* ctx, TrainPlan* tp, const void* in0, const voi
         CKR(launch_ingest(ctx, op, op.ingest_src == 0 ? in0 : in1, st));
     }
     const bool upd = !(flags & TRAIN_NO_STAT_UPDATE);
-    for (TBlock& b : tp->blocks) CKR(block_forward(ctx, tp, b, upd, st));
+    // the audio-encoder blocks (lane 1) run on the auxiliary stream beside the face encoder; the first consumer of the audio
+    // embedding (face_decoder_blocks.0.0; the embedding normalisation for SyncNet) waits for them
+    const bool aux = ctx->use_aux_stream && tp->blocks.size() > 1 && has_aux_lane(tp);
+    bool joined = !aux;
+    if (aux) {
+        CKR(ensure_aux_stream(ts));
+        CK(cudaEventRecord(ts->ev_aux_fork, st));
+        CK(cudaStreamWaitEvent(ts->s_aux, ts->ev_aux_fork, 0));
+    }
+    auto join_aux = [&]() -> int {
+        CK(cudaEventRecord(ts->ev_aux_join, ts->s_aux));
+        CK(cudaStreamWaitEvent(st, ts->ev_aux_join, 0));
+        joined = true;
+        return W2L_OK;
+    };
+    for (TBlock& b : tp->blocks) {
+        if (aux && b.lane == 1) { CKR(block_forward(ctx, tp, b, upd, ts->s_aux)); continue; }
+        if (!joined && starts_with(b.L.name, "face_decoder_blocks.")) CKR(join_aux());
+        CKR(block_forward(ctx, tp, b, upd, st));
+    }
+    if (!joined) CKR(join_aux());
     if (tp->net == W2L_NET_GENERATOR) {
         HeadParams hp;
         memset(&hp, 0, sizeof(hp));
@@ -831,13 +870,38 @@ static int train_backward(w2l_ctx* ctx, TrainPlan* tp, const float* d0, const fl
     }
     cudaStream_t s_wg = nullptr;
     if (wgrad && ctx->use_wg_stream) { CKR(ensure_wg_stream(ts)); s_wg = ts->s_wg; }
+    // audio-encoder blocks (lane 1): their backward chain starts at the gradient of the audio embedding — produced by
+    // face_decoder_blocks.0.0's dgrad (generator) or by the normalisation backward above (SyncNet) — and shares nothing with
+    // the face encoder's: it runs on the auxiliary stream, forked at that point, joined before the last block's hook
+    const bool aux = ctx->use_aux_stream && tp->blocks.size() > 1 && has_aux_lane(tp);
+    bool forked = false, waited = false, joined = false;
+    if (aux) {
+        CKR(ensure_aux_stream(ts));
+        if (tp->net != W2L_NET_GENERATOR) { CK(cudaEventRecord(ts->ev_aux_fork, st)); forked = true; }
+    }
+    auto join_aux = [&]() -> int {
+        if (waited && !joined) {
+            CK(cudaEventRecord(ts->ev_aux_join, ts->s_aux));
+            CK(cudaStreamWaitEvent(st, ts->ev_aux_join, 0));
+        }
+        joined = true;
+        return W2L_OK;
+    };
     for (size_t k = tp->blocks.size(); k-- > 0;) {
         TBlock& b = tp->blocks[k];
         // a frozen expert inside the generator step only needs the face branch: skip blocks whose gradient goes nowhere
         if (!wgrad && b.wgrad_only) continue;
-        CKR(block_backward(ctx, tp, b, wgrad, acc, st, s_wg, ts->ev_dz));
+        cudaStream_t bs = st;
+        if (aux && forked && b.lane == 1) {
+            if (!waited) { CK(cudaStreamWaitEvent(ts->s_aux, ts->ev_aux_fork, 0)); waited = true; }
+            bs = ts->s_aux;
+        }
+        CKR(block_backward(ctx, tp, b, wgrad, acc, bs, s_wg, ts->ev_dz));
+        if (aux && !forked && b.L.name == "face_decoder_blocks.0.0") { CK(cudaEventRecord(ts->ev_aux_fork, st)); forked = true; }
+        if (k == 0) CKR(join_aux());
         if (after_block) CKR((*after_block)(k));
     }
+    CKR(join_aux());
     if (s_wg) {   // join: whatever follows on `st` (Adam, the caller's optimizer, the next forward) sees every gradient
         CK(cudaEventRecord(ts->ev_wg, s_wg));
         CK(cudaStreamWaitEvent(st, ts->ev_wg, 0));

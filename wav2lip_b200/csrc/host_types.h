@@ -178,6 +178,7 @@ struct w2l_ctx {
     bool use_patch = true;   // W2L_DISABLE_HALO=1 turns the patch kernel off (A/B testing)
     bool use_bn256 = true;  // W2L_DISABLE_BN256=1
     bool use_mt2 = true;    // W2L_DISABLE_MT2=1
+    bool use_aux_stream = true; // W2L_DISABLE_AUXSTREAM=1: training audio-encoder blocks on the main stream
     bool use_wg_stream = true; // W2L_DISABLE_WGSTREAM=1: training wgrads on the main stream instead of a side stream
     bool use_rounds = true; // W2L_DISABLE_ROUNDS=1: rounds-based choice of 256-wide tiles for few-tile layers
     bool use_swap = true;   // W2L_DISABLE_SWAP=1: conv_swap_kernel (channel-major accumulator) for the 128-channel-tile layers

@@ -116,6 +116,7 @@ int w2l_create(int device, int precision, w2l_ctx** out) {
         ctx->use_swap = enabled("W2L_DISABLE_SWAP");
         ctx->use_rounds = enabled("W2L_DISABLE_ROUNDS");
         ctx->use_wg_stream = enabled("W2L_DISABLE_WGSTREAM");
+        ctx->use_aux_stream = enabled("W2L_DISABLE_AUXSTREAM");
         ctx->use_tma_epi = enabled("W2L_DISABLE_TMAEPI");
         ctx->use_ctfused = enabled("W2L_DISABLE_CTFUSED");
         ctx->use_rowstack = enabled("W2L_DISABLE_ROWSTACK");
